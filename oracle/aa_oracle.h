@@ -1,0 +1,180 @@
+/*
+ * aa_oracle.h -- CPU restatement of the audio-analyzer-rs frame-analysis path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library, and only as the checker or the timed CPU baseline.
+ *
+ * PARITY UNPINNED.  The reference is a Rust crate whose FFT arithmetic lives in
+ * the un-vendored crates realfft 3.5.0 / rustfft 6.4.1 (Cargo.lock:8799-8802,
+ * 9169-9172); no Rust toolchain exists in the build image, and the reference has
+ * no test, fixture or golden vector on this path.  This
+ * file therefore restates the reference source line by line (citations below are
+ * relative to /root/reference) and is cross-checked against an independent
+ * numpy restatement (tests/golden/make_golden.py) and a float64 DFT -- not
+ * against outputs of the reference binary.
+ *
+ * Arithmetic rules: every scalar the reference holds in f32 is held in `float`
+ * here, operations are performed in the reference's order, and the file must be
+ * compiled with -ffp-contract=off (no FMA contraction; Rust never contracts).
+ * ln/log2/cos go through libm (logf/log2f/cosf), as Rust's f32 methods do on
+ * Linux.
+ */
+#ifndef AA_ORACLE_H
+#define AA_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* feature-enable bits (same numeric values as include/aa_gpu.h) */
+#define AAO_FEAT_PITCH    1u  /* stft.rs:320-381  adaptive floor + extract_pitches  */
+#define AAO_FEAT_ONSET    2u  /* onset.rs:261-357 flux / burst / EMA / FluxTracker   */
+#define AAO_FEAT_CENTROID 4u  /* NEW (no reference): spectral centroid               */
+#define AAO_FEAT_TRACKER  8u  /* stft.rs:45-116   PitchTracker hysteresis            */
+
+/* flag bits in aao_features.flags */
+#define AAO_FLAG_FLUX_ONSET     1u  /* FluxTracker::update() returned true  onset.rs:355 */
+#define AAO_FLAG_BURST_ONSET    2u  /* max_excess > 3 && count >= 3         onset.rs:356 */
+#define AAO_FLAG_ONSET_DETECTED 4u  /* both                                 onset.rs:357 */
+#define AAO_FLAG_ENERGY_RISING  8u  /* energy > ema * 1.5 (post-update ema) onset.rs:373 */
+
+#define AAO_MAX_NOTES   8   /* stft.rs:452 */
+#define AAO_MAX_STABLE 16   /* bound on displayed PitchTracker tracks, see aa_oracle.c */
+
+typedef struct aao_config {
+    int32_t  n;               /* window size (stft.rs:170 = 2048, onset.rs:122 = 256)   */
+    int32_t  hop;             /* hop size    (stft.rs:169 = 512,  onset.rs:123 = 64)    */
+    float    sample_rate;     /* sr          (stft.rs:160)                              */
+    float    min_freq;        /* 24.0        (stft.rs:173)                              */
+    float    max_freq;        /* 10000.0     (stft.rs:174)                              */
+    float    noise_floor_db;  /* DynamicsOutput.noise_floor_db, default -96 (dynamics.rs:100) */
+    uint32_t features;        /* AAO_FEAT_* */
+} aao_config;
+
+/* One record per frame; 96 bytes; identical layout to aa_frame_features. */
+typedef struct aao_features {
+    uint32_t n_pitches;                     /* raw pitches from extract_pitches, <= 8      */
+    struct { float freq, score; } pitch[AAO_MAX_NOTES];
+    float    flux;                          /* onset.rs:261-291, zeroed if burst<2 (:337)  */
+    float    energy;                        /* onset.rs:276                                */
+    float    centroid;                      /* NEW                                         */
+    uint32_t burst_count;                   /* onset.rs:312-319                            */
+    float    max_excess;                    /* onset.rs:329-331                            */
+    uint32_t flags;                         /* AAO_FLAG_*                                  */
+    float    energy_ema;                    /* onset.rs:350 (value after this frame)       */
+} aao_features;
+
+/* PitchTracker output for one frame; 136 bytes; identical to aa_stable_pitches. */
+typedef struct aao_stable {
+    uint32_t n;
+    uint32_t reserved;
+    struct { float freq, score; } pitch[AAO_MAX_STABLE];
+} aao_stable;
+
+/* Per-frame diagnostics of extract_pitches used by the parity tests. */
+typedef struct aao_pitch_diag {
+    int32_t  n_peaks;            /* len(peak_bins)                      stft.rs:462-469 */
+    int32_t  n_scored;           /* peaks that passed the 5x floor gate stft.rs:479     */
+    int32_t  n_candidates;       /* after the 0.5*max cutoff            stft.rs:553-562 */
+    int32_t  n_out;              /* returned pitches                                    */
+    int32_t  out_bins[AAO_MAX_NOTES];   /* integer bin of each returned pitch           */
+    /* Smallest relative distance of any float-derived discrete decision from its
+     * flip point (comb-window integer boundaries, cutoff, ghost test, sort order,
+     * dedup distance, frequency range).  Decisions on raw magnitudes are exact
+     * given identical magnitudes and are not included.  */
+    float    min_margin;
+} aao_pitch_diag;
+
+/* ---- a1: window (stft.rs:641-648 == onset.rs:549-556) ------------------------- */
+void aao_hann_window(int n, float *w);
+
+/* ---- a3: FftProcessor (dsp/fft.rs:14-35,66-71) --------------------------------- */
+typedef struct aao_fft aao_fft;
+aao_fft *aao_fft_create(int n);                 /* n: power of two >= 4 */
+void     aao_fft_destroy(aao_fft *p);
+/* process_forward: `time` (n floats) is clobbered, `spec` receives n/2+1 interleaved
+ * (re,im) pairs, unnormalised; spec[0].im == spec[n/2].im == 0.  */
+void     aao_fft_forward(aao_fft *p, float *time, float *spec);
+/* float64 truth: same transform evaluated in double. */
+void     aao_rdft_f64(const double *x, int n, double *spec);
+
+/* ---- a4: magnitudes (stft.rs:314-318, num_complex norm == hypot) -------------- */
+void  aao_magnitudes(const float *spec, int half, float *mags);
+/* ---- a5: global floor (stft.rs:322-324, onset.rs:300-302) --------------------- */
+float aao_global_floor(float noise_floor_db, int half);
+
+/* ---- a6: adaptive per-bin floor (stft.rs:209-224, 326-367) -------------------- */
+typedef struct aao_pitch_floor aao_pitch_floor;
+aao_pitch_floor *aao_pitch_floor_create(int half);
+void aao_pitch_floor_destroy(aao_pitch_floor *s);
+void aao_pitch_floor_reset(aao_pitch_floor *s);
+void aao_pitch_floor_update(aao_pitch_floor *s, const float *mags, float global_floor,
+                            float *effective_floor);
+
+/* ---- a7: extract_pitches (stft.rs:443-620) ------------------------------------ */
+/* out_pairs: up to 8 (freq, score) pairs; peak_mask (optional): half bytes, 1 at
+ * each peak bin; diag optional.  Returns number of pitches. */
+int aao_extract_pitches(const float *mags, int half, float bin_width, float min_freq,
+                        float max_freq, const float *noise_floor, float *out_pairs,
+                        uint8_t *peak_mask, aao_pitch_diag *diag);
+
+/* ---- a8: PitchTracker (stft.rs:19-117) ---------------------------------------- */
+typedef struct aao_tracker aao_tracker;
+aao_tracker *aao_tracker_create(void);
+void aao_tracker_destroy(aao_tracker *t);
+void aao_tracker_reset(aao_tracker *t);
+/* returns number of stable pitches written to out_pairs (<= max_out pairs);
+ * the true count is returned even if it exceeds max_out. */
+int  aao_tracker_process(aao_tracker *t, const float *raw_pairs, int n_raw, int onset,
+                         float *out_pairs, int max_out);
+
+/* ---- a10-a12: onset frame body (onset.rs:149-186, 261-357, 47-84) ------------- */
+typedef struct aao_onset aao_onset;
+aao_onset *aao_onset_create(int half);
+void aao_onset_destroy(aao_onset *s);
+void aao_onset_reset(aao_onset *s);
+/* fills flux, energy, burst_count, max_excess, flags, energy_ema of *out */
+void aao_onset_frame(aao_onset *s, const float *mags, float global_floor, aao_features *out);
+
+/* ---- a13: spectral centroid (NEW, self-defined): sum(k*bw*m)/sum(m), f64 acc --- */
+float aao_centroid(const float *mags, int half, float bin_width);
+
+/* ---- a14: YIN-style lag search (NEW, self-defined; see aa_oracle.c) ------------ */
+/* Cumulative-mean-normalised difference over lags [min_lag, max_lag] on the raw
+ * (unwindowed) frame, evaluated in float64; returns the chosen integer lag (0 if
+ * none) and writes d'(lag) for lag in [0, max_lag] if cmnd != NULL. */
+int aao_yin_lag(const float *frame, int n, int min_lag, int max_lag, float threshold,
+                double *cmnd);
+
+/* ---- frame loop (stft.rs:273-438, onset.rs:244-543) on one offline clip ------- */
+/* T = (len - n)/hop + 1 frames (0 if len < n); frame t covers [t*hop, t*hop+n).
+ * Optional outputs may be NULL.  onset_in (optional, T bytes) feeds the
+ * PitchTracker's `onset` argument (stft.rs:387-390); NULL means never.
+ * If mags_in != NULL the FFT stage is skipped and the given magnitudes
+ * ([T][half]) are used instead (stage-isolated parity tests).
+ * Returns T.  */
+int64_t aao_analyze_clip(const aao_config *cfg, const float *samples, int64_t len,
+                         const float *mags_in, const uint8_t *onset_in,
+                         float *mags_out,            /* [T][half]            */
+                         float *floor_out,           /* [T][half] eff. floor */
+                         uint8_t *peak_mask_out,     /* [T][half]            */
+                         aao_features *feat_out,     /* [T]                  */
+                         aao_stable *stable_out,     /* [T]                  */
+                         aao_pitch_diag *diag_out);  /* [T]                  */
+
+int64_t aao_num_frames(int64_t len, int n, int hop);
+
+/* Clip-parallel driver for the timed CPU baseline: clips are contiguous,
+ * clip_len samples each; n_threads pthreads each take whole clips.  Only
+ * feature records (and optionally magnitudes) are produced. */
+int64_t aao_analyze_batch(const aao_config *cfg, const float *clips, int64_t n_clips,
+                          int64_t clip_len, int n_threads, float *mags_out,
+                          aao_features *feat_out, aao_stable *stable_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AA_ORACLE_H */

@@ -1,0 +1,316 @@
+"""ctypes binding of the CPU oracle (oracle/aa_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/aa_oracle.h.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  PARITY UNPINNED: the reference cannot be built here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libaa_oracle.so")
+
+FEAT_PITCH, FEAT_ONSET, FEAT_CENTROID, FEAT_TRACKER = 1, 2, 4, 8
+FLAG_FLUX_ONSET, FLAG_BURST_ONSET, FLAG_ONSET_DETECTED, FLAG_ENERGY_RISING = 1, 2, 4, 8
+MAX_NOTES, MAX_STABLE = 8, 16
+
+FEATURES_DTYPE = np.dtype(
+    [
+        ("n_pitches", "<u4"),
+        ("pitch", [("freq", "<f4"), ("score", "<f4")], (MAX_NOTES,)),
+        ("flux", "<f4"),
+        ("energy", "<f4"),
+        ("centroid", "<f4"),
+        ("burst_count", "<u4"),
+        ("max_excess", "<f4"),
+        ("flags", "<u4"),
+        ("energy_ema", "<f4"),
+    ]
+)
+assert FEATURES_DTYPE.itemsize == 96
+
+STABLE_DTYPE = np.dtype(
+    [
+        ("n", "<u4"),
+        ("reserved", "<u4"),
+        ("pitch", [("freq", "<f4"), ("score", "<f4")], (MAX_STABLE,)),
+    ]
+)
+assert STABLE_DTYPE.itemsize == 136
+
+DIAG_DTYPE = np.dtype(
+    [
+        ("n_peaks", "<i4"),
+        ("n_scored", "<i4"),
+        ("n_candidates", "<i4"),
+        ("n_out", "<i4"),
+        ("out_bins", "<i4", (MAX_NOTES,)),
+        ("min_margin", "<f4"),
+    ]
+)
+assert DIAG_DTYPE.itemsize == 52
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32),
+        ("hop", C.c_int32),
+        ("sample_rate", C.c_float),
+        ("min_freq", C.c_float),
+        ("max_freq", C.c_float),
+        ("noise_floor_db", C.c_float),
+        ("features", C.c_uint32),
+    ]
+
+
+def make_config(n=2048, hop=512, sample_rate=44100.0, min_freq=24.0, max_freq=10000.0,
+                noise_floor_db=-96.0, features=FEAT_PITCH | FEAT_ONSET | FEAT_CENTROID | FEAT_TRACKER):
+    return Config(n, hop, sample_rate, min_freq, max_freq, noise_floor_db, features)
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/aa_oracle.c -> oracle/libaa_oracle.so (gcc)."""
+    src = os.path.join(_HERE, "aa_oracle.c")
+    hdr = os.path.join(_HERE, "aa_oracle.h")
+    stale = (not os.path.exists(_SO)) or any(
+        os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr)
+    )
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libaa_oracle.so"],
+                              stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(_SO)
+    fp = C.POINTER(C.c_float)
+    dp = C.POINTER(C.c_double)
+    u8p = C.POINTER(C.c_uint8)
+    vp = C.c_void_p
+    L.aao_hann_window.argtypes = [C.c_int, fp]
+    L.aao_fft_create.restype = vp
+    L.aao_fft_create.argtypes = [C.c_int]
+    L.aao_fft_destroy.argtypes = [vp]
+    L.aao_fft_forward.argtypes = [vp, fp, fp]
+    L.aao_rdft_f64.argtypes = [dp, C.c_int, dp]
+    L.aao_magnitudes.argtypes = [fp, C.c_int, fp]
+    L.aao_global_floor.restype = C.c_float
+    L.aao_global_floor.argtypes = [C.c_float, C.c_int]
+    L.aao_pitch_floor_create.restype = vp
+    L.aao_pitch_floor_create.argtypes = [C.c_int]
+    L.aao_pitch_floor_destroy.argtypes = [vp]
+    L.aao_pitch_floor_reset.argtypes = [vp]
+    L.aao_pitch_floor_update.argtypes = [vp, fp, C.c_float, fp]
+    L.aao_extract_pitches.restype = C.c_int
+    L.aao_extract_pitches.argtypes = [fp, C.c_int, C.c_float, C.c_float, C.c_float, fp, fp, u8p, vp]
+    L.aao_tracker_create.restype = vp
+    L.aao_tracker_destroy.argtypes = [vp]
+    L.aao_tracker_reset.argtypes = [vp]
+    L.aao_tracker_process.restype = C.c_int
+    L.aao_tracker_process.argtypes = [vp, fp, C.c_int, C.c_int, fp, C.c_int]
+    L.aao_onset_create.restype = vp
+    L.aao_onset_create.argtypes = [C.c_int]
+    L.aao_onset_destroy.argtypes = [vp]
+    L.aao_onset_reset.argtypes = [vp]
+    L.aao_onset_frame.argtypes = [vp, fp, C.c_float, vp]
+    L.aao_centroid.restype = C.c_float
+    L.aao_centroid.argtypes = [fp, C.c_int, C.c_float]
+    L.aao_yin_lag.restype = C.c_int
+    L.aao_yin_lag.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_float, dp]
+    L.aao_num_frames.restype = C.c_int64
+    L.aao_num_frames.argtypes = [C.c_int64, C.c_int, C.c_int]
+    L.aao_analyze_clip.restype = C.c_int64
+    L.aao_analyze_clip.argtypes = [C.POINTER(Config), fp, C.c_int64, fp, u8p, fp, fp, u8p, vp, vp, vp]
+    L.aao_analyze_batch.restype = C.c_int64
+    L.aao_analyze_batch.argtypes = [C.POINTER(Config), fp, C.c_int64, C.c_int64, C.c_int, fp, vp, vp]
+    _lib = L
+    return L
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
+
+
+def _u8p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8)) if a is not None else None
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def hann_window(n: int) -> np.ndarray:
+    w = np.empty(n, np.float32)
+    lib().aao_hann_window(n, _fp(w))
+    return w
+
+
+def rfft_f32(x: np.ndarray) -> np.ndarray:
+    """FftProcessor::process_forward restatement; returns complex64[n/2+1]."""
+    x = np.ascontiguousarray(x, np.float32).copy()
+    n = x.shape[0]
+    p = lib().aao_fft_create(n)
+    if not p:
+        raise ValueError("n must be a power of two >= 4")
+    spec = np.empty(2 * (n // 2 + 1), np.float32)
+    lib().aao_fft_forward(p, _fp(x), _fp(spec))
+    lib().aao_fft_destroy(p)
+    return spec.view(np.complex64)
+
+
+def rdft_f64(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, np.float64)
+    n = x.shape[0]
+    spec = np.empty(2 * (n // 2 + 1), np.float64)
+    lib().aao_rdft_f64(x.ctypes.data_as(C.POINTER(C.c_double)), n,
+                       spec.ctypes.data_as(C.POINTER(C.c_double)))
+    return spec.view(np.complex128)
+
+
+def magnitudes(spec: np.ndarray) -> np.ndarray:
+    s = np.ascontiguousarray(spec, np.complex64).view(np.float32)
+    half = s.shape[0] // 2
+    m = np.empty(half, np.float32)
+    lib().aao_magnitudes(_fp(s), half, _fp(m))
+    return m
+
+
+def global_floor(noise_floor_db: float, half: int) -> float:
+    return float(lib().aao_global_floor(noise_floor_db, half))
+
+
+def extract_pitches(mags, floor, bin_width, min_freq=24.0, max_freq=10000.0):
+    """Returns (pairs[n,2] float32, peak_mask uint8[half], diag record)."""
+    mags = np.ascontiguousarray(mags, np.float32)
+    floor = np.ascontiguousarray(floor, np.float32)
+    half = mags.shape[0]
+    pairs = np.zeros((MAX_NOTES, 2), np.float32)
+    mask = np.zeros(half, np.uint8)
+    diag = np.zeros(1, DIAG_DTYPE)
+    n = lib().aao_extract_pitches(_fp(mags), half, bin_width, min_freq, max_freq, _fp(floor),
+                                  _fp(pairs), _u8p(mask), _vp(diag))
+    return pairs[:n].copy(), mask, diag[0]
+
+
+class PitchFloor:
+    def __init__(self, half):
+        self.half = half
+        self._p = lib().aao_pitch_floor_create(half)
+
+    def update(self, mags, gfloor):
+        mags = np.ascontiguousarray(mags, np.float32)
+        eff = np.empty(self.half, np.float32)
+        lib().aao_pitch_floor_update(self._p, _fp(mags), gfloor, _fp(eff))
+        return eff
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            lib().aao_pitch_floor_destroy(self._p)
+            self._p = None
+
+
+class Tracker:
+    def __init__(self):
+        self._p = lib().aao_tracker_create()
+
+    def process(self, pairs, onset=False):
+        pairs = np.ascontiguousarray(pairs, np.float32).reshape(-1, 2)
+        out = np.zeros((64, 2), np.float32)
+        n = lib().aao_tracker_process(self._p, _fp(pairs), pairs.shape[0], int(onset), _fp(out), 64)
+        return out[:n].copy()
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            lib().aao_tracker_destroy(self._p)
+            self._p = None
+
+
+class Onset:
+    def __init__(self, half):
+        self.half = half
+        self._p = lib().aao_onset_create(half)
+
+    def frame(self, mags, gfloor):
+        mags = np.ascontiguousarray(mags, np.float32)
+        out = np.zeros(1, FEATURES_DTYPE)
+        lib().aao_onset_frame(self._p, _fp(mags), gfloor, _vp(out))
+        return out[0]
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            lib().aao_onset_destroy(self._p)
+            self._p = None
+
+
+def centroid(mags, bin_width):
+    mags = np.ascontiguousarray(mags, np.float32)
+    return float(lib().aao_centroid(_fp(mags), mags.shape[0], bin_width))
+
+
+def yin_lag(frame, min_lag, max_lag, threshold=0.1):
+    frame = np.ascontiguousarray(frame, np.float32)
+    cm = np.zeros(max_lag + 1, np.float64)
+    lag = lib().aao_yin_lag(_fp(frame), frame.shape[0], min_lag, max_lag, threshold,
+                            cm.ctypes.data_as(C.POINTER(C.c_double)))
+    return lag, cm
+
+
+def num_frames(length, n, hop):
+    return int(lib().aao_num_frames(length, n, hop))
+
+
+def analyze_clip(cfg: Config, samples=None, mags_in=None, onset_in=None, want_mags=True,
+                 want_floor=False, want_peaks=False, want_diag=False):
+    """Run the frame loop on one clip.  Returns a dict of numpy arrays."""
+    half = cfg.n // 2 + 1
+    if mags_in is not None:
+        mags_in = np.ascontiguousarray(mags_in, np.float32)
+        T = mags_in.shape[0]
+        length = cfg.n + (T - 1) * cfg.hop
+        samples_arr = None
+    else:
+        samples_arr = np.ascontiguousarray(samples, np.float32)
+        length = samples_arr.shape[0]
+        T = num_frames(length, cfg.n, cfg.hop)
+    out = {"T": T}
+    if T <= 0:
+        return out
+    if onset_in is not None:
+        onset_in = np.ascontiguousarray(onset_in, np.uint8)
+    mags = np.empty((T, half), np.float32) if want_mags else None
+    floor = np.empty((T, half), np.float32) if want_floor else None
+    peaks = np.empty((T, half), np.uint8) if want_peaks else None
+    feat = np.zeros(T, FEATURES_DTYPE)
+    stable = np.zeros(T, STABLE_DTYPE)
+    diag = np.zeros(T, DIAG_DTYPE) if want_diag else None
+    got = lib().aao_analyze_clip(C.byref(cfg), _fp(samples_arr), length, _fp(mags_in), _u8p(onset_in),
+                                 _fp(mags), _fp(floor), _u8p(peaks), _vp(feat), _vp(stable), _vp(diag))
+    assert got == T
+    out.update(mags=mags, floor=floor, peaks=peaks, features=feat, stable=stable, diag=diag)
+    return out
+
+
+def analyze_batch(cfg: Config, clips: np.ndarray, n_threads: int, want_mags=False):
+    clips = np.ascontiguousarray(clips, np.float32)
+    n_clips, clip_len = clips.shape
+    T = num_frames(clip_len, cfg.n, cfg.hop)
+    half = cfg.n // 2 + 1
+    mags = np.empty((n_clips, T, half), np.float32) if want_mags else None
+    feat = np.zeros((n_clips, T), FEATURES_DTYPE)
+    stable = np.zeros((n_clips, T), STABLE_DTYPE)
+    total = lib().aao_analyze_batch(C.byref(cfg), _fp(clips), n_clips, clip_len, n_threads,
+                                    _fp(mags), _vp(feat), _vp(stable))
+    assert total == T * n_clips
+    return {"T": T, "mags": mags, "features": feat, "stable": stable}
