@@ -1,0 +1,810 @@
+// aa_api.cu -- the C ABI of libaa_gpu.so (include/aa_gpu.h): handles, tables, host
+// pipelines (H2D / kernel / D2H over clip groups) and the streaming ring.
+//
+// There is deliberately no CPU fallback anywhere in this file: if no sm_100 device is
+// usable every create call fails with AA_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "aa_internal.h"
+
+using namespace aa;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int g_device = 0;
+
+static aa_status fail(aa_status code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+static aa_status fail_cuda(cudaError_t e, const char *what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return AA_ERR_CUDA;
+}
+#define CU(call)                                           \
+    do {                                                   \
+        cudaError_t _e = (call);                           \
+        if (_e != cudaSuccess) return fail_cuda(_e, #call); \
+    } while (0)
+
+extern "C" AA_API const char *aa_last_error(void) { return g_err.c_str(); }
+extern "C" AA_API int32_t aa_version(void) { return 100; }
+
+static aa_status check_device(int *num_sms)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return fail(AA_ERR_NO_DEVICE, "no CUDA device visible (libaa_gpu has no CPU fallback)");
+    }
+    if (g_device >= count) return fail(AA_ERR_NO_DEVICE, "selected device index out of range");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, g_device));
+    if (prop.major != 10)
+        return fail(AA_ERR_NO_DEVICE, std::string("device '") + prop.name +
+                                          "' is not sm_100; libaa_gpu is built for sm_100a only");
+    CU(cudaSetDevice(g_device));
+    if (num_sms) *num_sms = prop.multiProcessorCount;
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_device_count(int32_t *count)
+{
+    if (!count) return fail(AA_ERR_INVALID, "count is null");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        c = 0;
+    }
+    *count = c;
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_set_device(int32_t device)
+{
+    if (device < 0) return fail(AA_ERR_INVALID, "negative device index");
+    g_device = device;
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(AA_ERR_INVALID, "out is null");
+    CU(cudaSetDevice(g_device));
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return AA_OK;
+}
+extern "C" AA_API aa_status aa_host_free(void *p)
+{
+    if (p) CU(cudaFreeHost(p));
+    return AA_OK;
+}
+extern "C" AA_API aa_status aa_device_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(AA_ERR_INVALID, "out is null");
+    CU(cudaSetDevice(g_device));
+    CU(cudaMalloc(out, bytes ? bytes : 1));
+    return AA_OK;
+}
+extern "C" AA_API aa_status aa_device_free(void *p)
+{
+    if (p) CU(cudaFree(p));
+    return AA_OK;
+}
+extern "C" AA_API aa_status aa_memcpy_h2d(void *dst, const void *src, size_t bytes)
+{
+    CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return AA_OK;
+}
+extern "C" AA_API aa_status aa_memcpy_d2h(void *dst, const void *src, size_t bytes)
+{
+    CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return AA_OK;
+}
+extern "C" AA_API aa_status aa_device_synchronize(void)
+{
+    CU(cudaDeviceSynchronize());
+    return AA_OK;
+}
+
+// ---------------------------------------------------------------------------
+// tables
+// ---------------------------------------------------------------------------
+static bool valid_n(int n) { return n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096; }
+
+struct DeviceTables {
+    void *mem = nullptr;
+    Tables tab{};
+};
+
+static aa_status build_tables(int n, DeviceTables *dt)
+{
+    const int n2 = n / 2, n4 = n / 4, half = n2 + 1;
+    const size_t nf2 = (size_t)n2 + n4 + n2;   // float2 entries: tw, pt, win2
+    const size_t bytes = nf2 * sizeof(float2) + (size_t)((half + 3) & ~3) * sizeof(float);
+    std::vector<unsigned char> host(bytes);
+    float2 *tw = reinterpret_cast<float2 *>(host.data());
+    float2 *pt = tw + n2;
+    float2 *win2 = pt + n4;
+    float *flux_w = reinterpret_cast<float *>(win2 + n2);
+    const double PI = 3.14159265358979323846;
+    for (int k = 0; k < n2; ++k) {
+        const double a = -2.0 * PI * (double)k / (double)n2;
+        tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    for (int k = 0; k < n4; ++k) {
+        // realfft: twiddle computed in f64, rounded to f32, then halved
+        const double a = -2.0 * PI * (double)k / (double)n;
+        pt[k] = make_float2((float)std::cos(a) * 0.5f, (float)std::sin(a) * 0.5f);
+    }
+    {
+        // periodic Hann exactly as stft.rs:641-648 (f32 throughout, libm cosf)
+        const float pi_f32 = 3.14159274101257324219f;
+        std::vector<float> w((size_t)n);
+        for (int i = 0; i < n; ++i) {
+            const float x = (float)i / (float)n;
+            w[(size_t)i] = 0.5f - 0.5f * cosf(2.0f * pi_f32 * x);
+        }
+        for (int m = 0; m < n2; ++m) win2[m] = make_float2(w[2 * (size_t)m], w[2 * (size_t)m + 1]);
+    }
+    for (int k = 0; k < half; ++k) flux_w[k] = 1.0f - ((float)k / (float)half);   // onset.rs:280
+
+    CU(cudaMalloc(&dt->mem, bytes));
+    CU(cudaMemcpy(dt->mem, host.data(), bytes, cudaMemcpyHostToDevice));
+    float2 *d = reinterpret_cast<float2 *>(dt->mem);
+    dt->tab.tw = d;
+    dt->tab.pt = d + n2;
+    dt->tab.win2 = d + n2 + n4;
+    dt->tab.flux_w = reinterpret_cast<const float *>(d + n2 + n4 + n2);
+    return AA_OK;
+}
+
+// ---------------------------------------------------------------------------
+// FftProcessor
+// ---------------------------------------------------------------------------
+struct aa_fft {
+    int n = 0, num_sms = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    DeviceTables dt;
+    float *d_in = nullptr, *d_out = nullptr;
+    int64_t cap = 0;
+};
+
+extern "C" AA_API aa_status aa_fft_create(int32_t n, aa_fft **out)
+{
+    if (!out) return fail(AA_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!valid_n(n)) return fail(AA_ERR_UNSUPPORTED, "FFT length must be one of 256, 512, 1024, 2048, 4096");
+    int sms = 0;
+    aa_status st = check_device(&sms);
+    if (st != AA_OK) return st;
+    aa_fft *h = new aa_fft();
+    h->n = n;
+    h->num_sms = sms;
+    h->device = g_device;
+    st = build_tables(n, &h->dt);
+    if (st != AA_OK) { delete h; return st; }
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { cudaFree(h->dt.mem); delete h; return fail_cuda(e, "cudaStreamCreate"); }
+    *out = h;
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_fft_destroy(aa_fft *h)
+{
+    if (!h) return AA_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    cudaFree(h->d_in);
+    cudaFree(h->d_out);
+    cudaFree(h->dt.mem);
+    delete h;
+    return AA_OK;
+}
+
+extern "C" AA_API int32_t aa_fft_len(const aa_fft *h) { return h ? h->n : 0; }
+
+static aa_status fft_reserve(aa_fft *h, int64_t batch)
+{
+    if (batch <= h->cap) return AA_OK;
+    cudaFree(h->d_in);
+    cudaFree(h->d_out);
+    h->d_in = h->d_out = nullptr;
+    h->cap = 0;
+    const size_t spec = 2 * (size_t)(h->n / 2 + 1);
+    const size_t per = std::max((size_t)h->n, spec);
+    CU(cudaMalloc(&h->d_in, sizeof(float) * per * (size_t)batch));
+    CU(cudaMalloc(&h->d_out, sizeof(float) * per * (size_t)batch));
+    h->cap = batch;
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_fft_forward_device(aa_fft *h, const float *in_dev, int64_t batch,
+                                                  float *out_dev, void *stream)
+{
+    if (!h || !in_dev || !out_dev || batch < 0) return fail(AA_ERR_INVALID, "aa_fft_forward_device: bad argument");
+    if (((uintptr_t)in_dev & 7u) || ((uintptr_t)out_dev & 7u))
+        return fail(AA_ERR_INVALID, "aa_fft_forward_device: buffers must be 8-byte aligned");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    CU(launch_fft_forward(h->n, h->dt.tab, in_dev, batch, out_dev, h->num_sms, s));
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_fft_forward(aa_fft *h, const float *in_host, int64_t batch, float *out_host)
+{
+    if (!h || !in_host || !out_host || batch < 0) return fail(AA_ERR_INVALID, "aa_fft_forward: bad argument");
+    if (batch == 0) return AA_OK;
+    CU(cudaSetDevice(h->device));
+    aa_status st = fft_reserve(h, batch);
+    if (st != AA_OK) return st;
+    const size_t spec = 2 * (size_t)(h->n / 2 + 1);
+    CU(cudaMemcpyAsync(h->d_in, in_host, sizeof(float) * (size_t)h->n * (size_t)batch, cudaMemcpyHostToDevice,
+                       h->stream));
+    CU(launch_fft_forward(h->n, h->dt.tab, h->d_in, batch, h->d_out, h->num_sms, h->stream));
+    CU(cudaMemcpyAsync(out_host, h->d_out, sizeof(float) * spec * (size_t)batch, cudaMemcpyDeviceToHost,
+                       h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_fft_inverse_device(aa_fft *h, const float *spec_dev, int64_t batch,
+                                                  float *out_dev, void *stream)
+{
+    if (!h || !spec_dev || !out_dev || batch < 0) return fail(AA_ERR_INVALID, "aa_fft_inverse_device: bad argument");
+    if (((uintptr_t)spec_dev & 7u) || ((uintptr_t)out_dev & 7u))
+        return fail(AA_ERR_INVALID, "aa_fft_inverse_device: buffers must be 8-byte aligned");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    CU(launch_fft_inverse(h->n, h->dt.tab, spec_dev, batch, out_dev, h->num_sms, s));
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_fft_inverse(aa_fft *h, const float *spec_host, int64_t batch, float *out_host)
+{
+    if (!h || !spec_host || !out_host || batch < 0) return fail(AA_ERR_INVALID, "aa_fft_inverse: bad argument");
+    if (batch == 0) return AA_OK;
+    CU(cudaSetDevice(h->device));
+    aa_status st = fft_reserve(h, batch);
+    if (st != AA_OK) return st;
+    const size_t spec = 2 * (size_t)(h->n / 2 + 1);
+    CU(cudaMemcpyAsync(h->d_in, spec_host, sizeof(float) * spec * (size_t)batch, cudaMemcpyHostToDevice, h->stream));
+    CU(launch_fft_inverse(h->n, h->dt.tab, h->d_in, batch, h->d_out, h->num_sms, h->stream));
+    CU(cudaMemcpyAsync(out_host, h->d_out, sizeof(float) * (size_t)h->n * (size_t)batch, cudaMemcpyDeviceToHost,
+                       h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return AA_OK;
+}
+
+// ---------------------------------------------------------------------------
+// analyzer
+// ---------------------------------------------------------------------------
+extern "C" AA_API void aa_config_default_pitch(aa_config *cfg, float sample_rate)
+{
+    if (!cfg) return;
+    cfg->n = 2048;               // stft.rs:170
+    cfg->hop = 512;              // stft.rs:169
+    cfg->sample_rate = sample_rate;
+    cfg->min_freq = 24.0f;       // stft.rs:173
+    cfg->max_freq = 10000.0f;    // stft.rs:174
+    cfg->noise_floor_db = -96.0f;  // dynamics.rs:100
+    cfg->features = AA_FEAT_PITCH | AA_FEAT_TRACKER;
+}
+
+extern "C" AA_API void aa_config_default_onset(aa_config *cfg, float sample_rate)
+{
+    if (!cfg) return;
+    cfg->n = 256;                // onset.rs:122
+    cfg->hop = 64;               // onset.rs:123
+    cfg->sample_rate = sample_rate;
+    cfg->min_freq = 24.0f;
+    cfg->max_freq = 10000.0f;
+    cfg->noise_floor_db = -96.0f;
+    cfg->features = AA_FEAT_ONSET;
+}
+
+static aa_status validate_config(const aa_config *cfg)
+{
+    if (!cfg) return fail(AA_ERR_INVALID, "config is null");
+    if (!valid_n(cfg->n)) return fail(AA_ERR_UNSUPPORTED, "window size must be one of 256, 512, 1024, 2048, 4096");
+    if (cfg->hop != cfg->n / 4)
+        return fail(AA_ERR_UNSUPPORTED, "hop must be n/4 (the reference geometry, stft.rs:169 / onset.rs:123)");
+    if (!(cfg->sample_rate > 0.0f)) return fail(AA_ERR_INVALID, "sample_rate must be positive");
+    if (cfg->features & ~AA_FEAT_ALL) return fail(AA_ERR_INVALID, "unknown feature bits");
+    if ((cfg->features & AA_FEAT_TRACKER) && !(cfg->features & AA_FEAT_PITCH))
+        return fail(AA_ERR_INVALID, "AA_FEAT_TRACKER requires AA_FEAT_PITCH");
+    return AA_OK;
+}
+
+extern "C" AA_API int64_t aa_num_frames(const aa_config *cfg, int64_t clip_len)
+{
+    if (!cfg || cfg->n <= 0 || cfg->hop <= 0 || clip_len < cfg->n) return 0;
+    return (clip_len - cfg->n) / cfg->hop + 1;
+}
+
+static void fill_params(const aa_config &cfg, const Tables &tab, AnalyzeParams *p)
+{
+    const int half = cfg.n / 2 + 1;
+    p->tab = tab;
+    p->n = cfg.n;
+    p->hop = cfg.hop;
+    p->half = half;
+    p->bin_width = cfg.sample_rate / (float)cfg.n;                          // stft.rs:320
+    p->min_freq = cfg.min_freq;
+    p->max_freq = cfg.max_freq;
+    p->global_floor = powf(10.0f, cfg.noise_floor_db / 20.0f) * (float)half / 2.0f;  // stft.rs:323-324
+    // stft.rs:454-455 (`as usize` saturates negatives to 0)
+    float mb = ceilf(cfg.min_freq / p->bin_width);
+    long long minb = mb > 0.0f ? (mb < 1e9f ? (long long)mb : 1000000000LL) : 0;
+    if (minb < 1) minb = 1;
+    float xb = floorf(cfg.max_freq / p->bin_width);
+    long long maxb = xb > 0.0f ? (xb < 1e9f ? (long long)xb : 1000000000LL) : 0;
+    const long long hs2 = half >= 2 ? half - 2 : 0;
+    if (maxb > hs2) maxb = hs2;
+    p->min_bin = (int)minb;
+    p->max_bin = (int)maxb;
+    p->features_mask = cfg.features;
+}
+
+struct StageSlot {
+    float *in = nullptr;
+    size_t in_cap = 0;
+    float *mags = nullptr;
+    size_t mags_cap = 0;
+    aa_frame_features *feat = nullptr;
+    aa_stable_pitches *stable = nullptr;
+    aa_clip_summary *summ = nullptr;
+    uint8_t *onset = nullptr;
+    float *dbg_floor = nullptr;
+    uint8_t *dbg_peaks = nullptr;
+    size_t frames_cap = 0, clips_cap = 0, dbgf_cap = 0, dbgp_cap = 0, onset_cap = 0;
+    cudaEvent_t h2d_done = nullptr, k_done = nullptr, d2h_done = nullptr;
+};
+
+struct aa_analyzer {
+    aa_config cfg{};
+    int device = 0, num_sms = 0;
+    DeviceTables dt;
+    cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    StageSlot slot[2];
+    int64_t launches = 0;
+};
+
+extern "C" AA_API aa_status aa_analyzer_create(const aa_config *cfg, aa_analyzer **out)
+{
+    if (!out) return fail(AA_ERR_INVALID, "out is null");
+    *out = nullptr;
+    aa_status st = validate_config(cfg);
+    if (st != AA_OK) return st;
+    int sms = 0;
+    st = check_device(&sms);
+    if (st != AA_OK) return st;
+    aa_analyzer *h = new aa_analyzer();
+    h->cfg = *cfg;
+    h->device = g_device;
+    h->num_sms = sms;
+    st = build_tables(cfg->n, &h->dt);
+    if (st != AA_OK) { delete h; return st; }
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) {
+        aa_analyzer_destroy(h);
+        return fail_cuda(e, "cudaStreamCreate");
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&h->slot[i].h2d_done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->slot[i].k_done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->slot[i].d2h_done, cudaEventDisableTiming);
+    }
+    *out = h;
+    return AA_OK;
+}
+
+static void free_slot(StageSlot &s)
+{
+    cudaFree(s.in); cudaFree(s.mags); cudaFree(s.feat); cudaFree(s.stable); cudaFree(s.summ);
+    cudaFree(s.onset); cudaFree(s.dbg_floor); cudaFree(s.dbg_peaks);
+    if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+    if (s.k_done) cudaEventDestroy(s.k_done);
+    if (s.d2h_done) cudaEventDestroy(s.d2h_done);
+    s = StageSlot();
+}
+
+extern "C" AA_API aa_status aa_analyzer_destroy(aa_analyzer *h)
+{
+    if (!h) return AA_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) free_slot(h->slot[i]);
+    if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    cudaFree(h->dt.mem);
+    delete h;
+    return AA_OK;
+}
+
+extern "C" AA_API int64_t aa_analyzer_last_launches(const aa_analyzer *h) { return h ? h->launches : 0; }
+
+static aa_status analyze_device_impl(aa_analyzer *h, const float *clips_dev, int64_t n_clips, int64_t clip_len,
+                                     int64_t clip_stride, const uint8_t *onset_in_dev, const aa_outputs *out,
+                                     float *state, cudaStream_t s, int64_t *launches)
+{
+    const int64_t T = aa_num_frames(&h->cfg, clip_len);
+    if (n_clips == 0 || T == 0) return AA_OK;
+    if (((uintptr_t)clips_dev & 15u) || (clip_stride & 3))
+        return fail(AA_ERR_INVALID,
+                    "clips must be 16-byte aligned and clip_stride a multiple of 4 samples (TMA bulk copy)");
+    if (out->summaries && !out->features) return fail(AA_ERR_INVALID, "summaries need the features output");
+    AnalyzeParams p{};
+    fill_params(h->cfg, h->dt.tab, &p);
+    p.clips = clips_dev;
+    p.n_clips = n_clips;
+    p.clip_len = clip_len;
+    p.clip_stride = clip_stride;
+    p.T = T;
+    p.onset_in = onset_in_dev;
+    p.mags = out->mags;
+    p.features = out->features;
+    p.stable = out->stable;
+    p.dbg_floor = out->dbg_floor;
+    p.dbg_peaks = out->dbg_peaks;
+    p.state = state;
+    CU(launch_analyze(p, s));
+    ++*launches;
+    if (out->summaries) {
+        CU(launch_summaries(out->features, n_clips, T, out->summaries, s));
+        ++*launches;
+    }
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_analyze_device(aa_analyzer *h, const float *clips_dev, int64_t n_clips,
+                                              int64_t clip_len, int64_t clip_stride,
+                                              const uint8_t *onset_in_dev, const aa_outputs *out_dev,
+                                              void *stream)
+{
+    if (!h || !clips_dev || !out_dev || n_clips < 0 || clip_len < 0 || clip_stride < 0)
+        return fail(AA_ERR_INVALID, "aa_analyze_device: bad argument");
+    CU(cudaSetDevice(h->device));
+    h->launches = 0;
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->s_compute;
+    return analyze_device_impl(h, clips_dev, n_clips, clip_len, clip_stride, onset_in_dev, out_dev, nullptr, s,
+                               &h->launches);
+}
+
+template <typename Tp>
+static aa_status grow(Tp **p, size_t *cap, size_t need)
+{
+    if (need <= *cap) return AA_OK;
+    cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    CU(cudaMalloc(p, need * sizeof(Tp)));
+    *cap = need;
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_analyze_host(aa_analyzer *h, const float *clips_host, int64_t n_clips,
+                                            int64_t clip_len, int64_t clip_stride,
+                                            const uint8_t *onset_in_host, const aa_outputs *out_host)
+{
+    if (!h || !clips_host || !out_host || n_clips < 0 || clip_len < 0 || clip_stride < 0)
+        return fail(AA_ERR_INVALID, "aa_analyze_host: bad argument");
+    CU(cudaSetDevice(h->device));
+    h->launches = 0;
+    const int64_t T = aa_num_frames(&h->cfg, clip_len);
+    if (n_clips == 0 || T == 0) return AA_OK;
+    if (clip_stride & 3) return fail(AA_ERR_INVALID, "clip_stride must be a multiple of 4 samples");
+    if (out_host->summaries && !out_host->features)
+        return fail(AA_ERR_INVALID, "summaries need the features output");
+    const int half = h->cfg.n / 2 + 1;
+
+    // clip groups: at least ~2 waves of CTAs per group when there is enough work, at most 8 groups
+    int64_t n_groups = n_clips / (2 * (int64_t)h->num_sms);
+    n_groups = std::max<int64_t>(1, std::min<int64_t>(8, n_groups));
+    const int64_t G = (n_clips + n_groups - 1) / n_groups;
+
+    for (int64_t g = 0, c0 = 0; c0 < n_clips; ++g, c0 += G) {
+        const int64_t nc = std::min(G, n_clips - c0);
+        StageSlot &sl = h->slot[g & 1];
+        // slot reuse: its previous D2H must have drained
+        if (g >= 2) CU(cudaEventSynchronize(sl.d2h_done));
+        const size_t span = (size_t)((nc - 1) * clip_stride + clip_len);
+        const size_t span_pad = (span + 3) & ~(size_t)3;
+        const size_t frames = (size_t)(nc * T);
+        aa_status st;
+        if ((st = grow(&sl.in, &sl.in_cap, span_pad)) != AA_OK) return st;
+        if (out_host->mags && (st = grow(&sl.mags, &sl.mags_cap, frames * half)) != AA_OK) return st;
+        if (frames > sl.frames_cap) {
+            cudaFree(sl.feat); cudaFree(sl.stable);
+            sl.feat = nullptr; sl.stable = nullptr; sl.frames_cap = 0;
+            CU(cudaMalloc(&sl.feat, frames * sizeof(aa_frame_features)));
+            CU(cudaMalloc(&sl.stable, frames * sizeof(aa_stable_pitches)));
+            sl.frames_cap = frames;
+        }
+        if (out_host->summaries && (st = grow(&sl.summ, &sl.clips_cap, (size_t)nc)) != AA_OK) return st;
+        if (out_host->dbg_floor && (st = grow(&sl.dbg_floor, &sl.dbgf_cap, frames * half)) != AA_OK) return st;
+        if (out_host->dbg_peaks && (st = grow(&sl.dbg_peaks, &sl.dbgp_cap, frames * half)) != AA_OK) return st;
+        if (onset_in_host && (st = grow(&sl.onset, &sl.onset_cap, frames)) != AA_OK) return st;
+
+        // H2D (the kernel that last read this slot's input has finished: d2h_done above implies k_done)
+        CU(cudaMemcpyAsync(sl.in, clips_host + c0 * clip_stride, span * sizeof(float), cudaMemcpyHostToDevice,
+                           h->s_h2d));
+        if (onset_in_host)
+            CU(cudaMemcpyAsync(sl.onset, onset_in_host + c0 * T, frames, cudaMemcpyHostToDevice, h->s_h2d));
+        CU(cudaEventRecord(sl.h2d_done, h->s_h2d));
+
+        // kernels
+        CU(cudaStreamWaitEvent(h->s_compute, sl.h2d_done, 0));
+        aa_outputs od{};
+        od.mags = out_host->mags ? sl.mags : nullptr;
+        od.features = out_host->features || out_host->summaries ? sl.feat : nullptr;
+        od.stable = out_host->stable ? sl.stable : nullptr;
+        od.summaries = out_host->summaries ? sl.summ : nullptr;
+        od.dbg_floor = out_host->dbg_floor ? sl.dbg_floor : nullptr;
+        od.dbg_peaks = out_host->dbg_peaks ? sl.dbg_peaks : nullptr;
+        st = analyze_device_impl(h, sl.in, nc, clip_len, clip_stride, onset_in_host ? sl.onset : nullptr, &od,
+                                 nullptr, h->s_compute, &h->launches);
+        if (st != AA_OK) return st;
+        CU(cudaEventRecord(sl.k_done, h->s_compute));
+
+        // D2H
+        CU(cudaStreamWaitEvent(h->s_d2h, sl.k_done, 0));
+        const size_t f0 = (size_t)(c0 * T);
+        if (out_host->mags)
+            CU(cudaMemcpyAsync(out_host->mags + f0 * half, sl.mags, frames * half * sizeof(float),
+                               cudaMemcpyDeviceToHost, h->s_d2h));
+        if (out_host->features)
+            CU(cudaMemcpyAsync(out_host->features + f0, sl.feat, frames * sizeof(aa_frame_features),
+                               cudaMemcpyDeviceToHost, h->s_d2h));
+        if (out_host->stable)
+            CU(cudaMemcpyAsync(out_host->stable + f0, sl.stable, frames * sizeof(aa_stable_pitches),
+                               cudaMemcpyDeviceToHost, h->s_d2h));
+        if (out_host->summaries)
+            CU(cudaMemcpyAsync(out_host->summaries + c0, sl.summ, (size_t)nc * sizeof(aa_clip_summary),
+                               cudaMemcpyDeviceToHost, h->s_d2h));
+        if (out_host->dbg_floor)
+            CU(cudaMemcpyAsync(out_host->dbg_floor + f0 * half, sl.dbg_floor, frames * half * sizeof(float),
+                               cudaMemcpyDeviceToHost, h->s_d2h));
+        if (out_host->dbg_peaks)
+            CU(cudaMemcpyAsync(out_host->dbg_peaks + f0 * half, sl.dbg_peaks, frames * half,
+                               cudaMemcpyDeviceToHost, h->s_d2h));
+        CU(cudaEventRecord(sl.d2h_done, h->s_d2h));
+        // the next H2D into the *other* slot may start immediately; H2D into this slot
+        // waits for d2h_done at the top of the loop
+    }
+    CU(cudaStreamSynchronize(h->s_d2h));
+    CU(cudaStreamSynchronize(h->s_compute));
+    return AA_OK;
+}
+
+// ---------------------------------------------------------------------------
+// streaming
+// ---------------------------------------------------------------------------
+struct aa_stream {
+    aa_analyzer *an = nullptr;
+    int n = 0, hop = 0, half = 0;
+    // device sample buffers (ping-pong linear buffers) and host pinned staging
+    float *d_buf[2] = {nullptr, nullptr};
+    int cur = 0;
+    int64_t cap = 0;          // samples per device buffer
+    int64_t rd = 0, wr = 0;   // read / write positions in d_buf[cur]
+    float *h_stage = nullptr; // pinned, cap samples
+    int64_t stage_pos = 0;
+    // analyzer state, outputs
+    float *d_state = nullptr;
+    aa_frame_features *d_feat = nullptr;
+    aa_stable_pitches *d_stab = nullptr;
+    uint8_t *d_onset = nullptr;
+    uint8_t *h_onset = nullptr;          // pinned
+    aa_frame_features *h_feat = nullptr; // pinned ring
+    aa_stable_pitches *h_stab = nullptr; // pinned ring
+    int64_t max_frames_per_push = 0;
+    int64_t out_cap = 0;                 // frames in the host result ring
+    int64_t out_head = 0, out_count = 0; // ring of completed frames
+    int64_t frame_index = 0;             // total frames produced
+    bool onset_pending = false;
+    cudaStream_t s = nullptr;
+};
+
+extern "C" AA_API aa_status aa_stream_destroy(aa_stream *h)
+{
+    if (!h) return AA_OK;
+    if (h->an) cudaSetDevice(h->an->device);
+    if (h->s) { cudaStreamSynchronize(h->s); cudaStreamDestroy(h->s); }
+    cudaFree(h->d_buf[0]); cudaFree(h->d_buf[1]); cudaFree(h->d_state); cudaFree(h->d_feat);
+    cudaFree(h->d_stab); cudaFree(h->d_onset);
+    cudaFreeHost(h->h_stage); cudaFreeHost(h->h_onset); cudaFreeHost(h->h_feat); cudaFreeHost(h->h_stab);
+    if (h->an) aa_analyzer_destroy(h->an);
+    delete h;
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_stream_create(const aa_config *cfg, aa_stream **out)
+{
+    if (!out) return fail(AA_ERR_INVALID, "out is null");
+    *out = nullptr;
+    aa_analyzer *an = nullptr;
+    aa_status st = aa_analyzer_create(cfg, &an);
+    if (st != AA_OK) return st;
+    aa_stream *h = new aa_stream();
+    h->an = an;
+    h->n = cfg->n;
+    h->hop = cfg->hop;
+    h->half = cfg->n / 2 + 1;
+    // the reference ring is max(8192, 4*window) samples (stft.rs:171, onset.rs:124); one push may carry
+    // up to that much, the device buffer holds 8x as much so compaction is rare
+    const int64_t ring = std::max<int64_t>(8192, 4 * (int64_t)cfg->n);
+    h->cap = 8 * ring;
+    h->max_frames_per_push = ring / cfg->hop + 4;
+    h->out_cap = 4 * h->max_frames_per_push;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    ok(cudaStreamCreateWithFlags(&h->s, cudaStreamNonBlocking));
+    ok(cudaMalloc(&h->d_buf[0], sizeof(float) * h->cap));
+    ok(cudaMalloc(&h->d_buf[1], sizeof(float) * h->cap));
+    ok(cudaMalloc(&h->d_state, sizeof(float) * state_floats(h->half)));
+    ok(cudaMalloc(&h->d_feat, sizeof(aa_frame_features) * h->max_frames_per_push));
+    ok(cudaMalloc(&h->d_stab, sizeof(aa_stable_pitches) * h->max_frames_per_push));
+    ok(cudaMalloc(&h->d_onset, h->max_frames_per_push));
+    ok(cudaHostAlloc(&h->h_stage, sizeof(float) * ring, cudaHostAllocDefault));
+    ok(cudaHostAlloc(&h->h_onset, h->max_frames_per_push, cudaHostAllocDefault));
+    ok(cudaHostAlloc(&h->h_feat, sizeof(aa_frame_features) * h->out_cap, cudaHostAllocDefault));
+    ok(cudaHostAlloc(&h->h_stab, sizeof(aa_stable_pitches) * h->out_cap, cudaHostAllocDefault));
+    if (e == cudaSuccess) ok(cudaMemsetAsync(h->d_state, 0, sizeof(float) * state_floats(h->half), h->s));
+    if (e == cudaSuccess) ok(cudaStreamSynchronize(h->s));
+    if (e != cudaSuccess) {
+        aa_stream_destroy(h);
+        return fail_cuda(e, "aa_stream_create");
+    }
+    *out = h;
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_stream_reset(aa_stream *h)
+{
+    if (!h) return fail(AA_ERR_INVALID, "stream is null");
+    CU(cudaSetDevice(h->an->device));
+    CU(cudaStreamSynchronize(h->s));
+    CU(cudaMemsetAsync(h->d_state, 0, sizeof(float) * state_floats(h->half), h->s));
+    CU(cudaStreamSynchronize(h->s));
+    h->rd = h->wr = 0;
+    h->cur = 0;
+    h->out_head = h->out_count = 0;
+    h->frame_index = 0;
+    h->onset_pending = false;
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_stream_set_noise_floor_db(aa_stream *h, float db)
+{
+    if (!h) return fail(AA_ERR_INVALID, "stream is null");
+    h->an->cfg.noise_floor_db = db;   // picked up by fill_params at the next push (stft.rs:322)
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_stream_signal_onset(aa_stream *h)
+{
+    if (!h) return fail(AA_ERR_INVALID, "stream is null");
+    h->onset_pending = true;          // consumed by the next frame (stft.rs:387 swap(false))
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_stream_push(aa_stream *h, const float *samples, int32_t count)
+{
+    if (!h || (!samples && count > 0) || count < 0) return fail(AA_ERR_INVALID, "aa_stream_push: bad argument");
+    if (count == 0) return AA_OK;
+    const int64_t ring = h->cap / 8;
+    if (count > ring) return fail(AA_ERR_OVERFLOW, "aa_stream_push: more samples than the ring holds in one push");
+    CU(cudaSetDevice(h->an->device));
+    // previous push fully drained (results already in the host ring) before staging is reused
+    CU(cudaStreamSynchronize(h->s));
+
+    // compact: move the unread tail to the other buffer when the linear buffer would overflow
+    if (h->wr + count > h->cap) {
+        const int64_t avail = h->wr - h->rd;
+        // keep the read position 16-byte aligned for the TMA bulk copy
+        const int64_t rd_al = h->rd & ~(int64_t)3;
+        const int64_t lead = h->rd - rd_al;
+        CU(cudaMemcpyAsync(h->d_buf[h->cur ^ 1], h->d_buf[h->cur] + rd_al, sizeof(float) * (size_t)(avail + lead),
+                           cudaMemcpyDeviceToDevice, h->s));
+        h->cur ^= 1;
+        h->rd = lead;
+        h->wr = lead + avail;
+    }
+    std::memcpy(h->h_stage, samples, sizeof(float) * (size_t)count);
+    CU(cudaMemcpyAsync(h->d_buf[h->cur] + h->wr, h->h_stage, sizeof(float) * (size_t)count,
+                       cudaMemcpyHostToDevice, h->s));
+    h->wr += count;
+
+    const int64_t avail = h->wr - h->rd;
+    if (avail < h->n) return AA_OK;
+    int64_t T = (avail - h->n) / h->hop + 1;
+    if (T > h->max_frames_per_push) T = h->max_frames_per_push;
+    if (h->out_count + T > h->out_cap)
+        return fail(AA_ERR_OVERFLOW, "aa_stream_push: result ring full, call aa_stream_poll");
+    if (h->rd & 3) return fail(AA_ERR_INVALID, "aa_stream: hop must keep the read position 16-byte aligned");
+
+    const bool use_onset = (h->an->cfg.features & AA_FEAT_TRACKER) != 0;
+    if (use_onset) {
+        std::memset(h->h_onset, 0, (size_t)T);
+        if (h->onset_pending) h->h_onset[0] = 1;
+        h->onset_pending = false;
+        CU(cudaMemcpyAsync(h->d_onset, h->h_onset, (size_t)T, cudaMemcpyHostToDevice, h->s));
+    }
+    aa_outputs od{};
+    od.features = h->d_feat;
+    od.stable = h->d_stab;
+    const int64_t clip_len = h->n + (T - 1) * h->hop;
+    int64_t launches = 0;
+    aa_status st = analyze_device_impl(h->an, h->d_buf[h->cur] + h->rd, 1, clip_len, (clip_len + 3) & ~(int64_t)3,
+                                       use_onset ? h->d_onset : nullptr, &od, h->d_state, h->s, &launches);
+    if (st != AA_OK) return st;
+    // results into the host ring (two segments if it wraps)
+    int64_t tail = (h->out_head + h->out_count) % h->out_cap;
+    int64_t first = std::min(T, h->out_cap - tail);
+    CU(cudaMemcpyAsync(h->h_feat + tail, h->d_feat, sizeof(aa_frame_features) * (size_t)first,
+                       cudaMemcpyDeviceToHost, h->s));
+    CU(cudaMemcpyAsync(h->h_stab + tail, h->d_stab, sizeof(aa_stable_pitches) * (size_t)first,
+                       cudaMemcpyDeviceToHost, h->s));
+    if (first < T) {
+        CU(cudaMemcpyAsync(h->h_feat, h->d_feat + first, sizeof(aa_frame_features) * (size_t)(T - first),
+                           cudaMemcpyDeviceToHost, h->s));
+        CU(cudaMemcpyAsync(h->h_stab, h->d_stab + first, sizeof(aa_stable_pitches) * (size_t)(T - first),
+                           cudaMemcpyDeviceToHost, h->s));
+    }
+    h->out_count += T;
+    h->rd += T * h->hop;
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_stream_poll(aa_stream *h, aa_stream_frame *out, int32_t max, int32_t *n_out)
+{
+    if (!h || !n_out || (max > 0 && !out)) return fail(AA_ERR_INVALID, "aa_stream_poll: bad argument");
+    *n_out = 0;
+    if (h->out_count == 0 || max <= 0) return AA_OK;
+    CU(cudaSetDevice(h->an->device));
+    CU(cudaStreamSynchronize(h->s));
+    int32_t n = (int32_t)std::min<int64_t>(max, h->out_count);
+    for (int32_t i = 0; i < n; ++i) {
+        const int64_t idx = (h->out_head + i) % h->out_cap;
+        out[i].frame_index = h->frame_index + i;
+        out[i].features = h->h_feat[idx];
+        out[i].stable = h->h_stab[idx];
+    }
+    h->out_head = (h->out_head + n) % h->out_cap;
+    h->out_count -= n;
+    h->frame_index += n;
+    *n_out = n;
+    return AA_OK;
+}
+
+// ---------------------------------------------------------------------------
+// synthetic clips
+// ---------------------------------------------------------------------------
+extern "C" AA_API aa_status aa_synth_clips_device(float *clips_dev, int64_t n_clips, int64_t clip_len,
+                                                  int64_t clip_stride, float sample_rate, uint64_t seed,
+                                                  void *stream)
+{
+    if (!clips_dev || n_clips < 0 || clip_len < 0 || clip_stride < clip_len || !(sample_rate > 0.0f))
+        return fail(AA_ERR_INVALID, "aa_synth_clips_device: bad argument");
+    aa_status st = check_device(nullptr);
+    if (st != AA_OK) return st;
+    CU(launch_synth(clips_dev, n_clips, clip_len, clip_stride, sample_rate, seed, (cudaStream_t)stream));
+    return AA_OK;
+}

@@ -1,0 +1,240 @@
+// aa_fft.cuh -- register-resident Stockham FFT building blocks (sm_100a).
+//
+// Replaces realfft::RealToComplex::process_with_scratch as called from
+// FftProcessor::process_forward (reference src/dsp/fft.rs:33, 66-71): an n-point
+// real transform is computed as an n/2-point complex FFT of z[m] = x[2m] + i x[2m+1]
+// followed by a split post-pass.
+//
+// Thread mapping (verified by tools/stockham_model.py): a CTA of NT = N2/E threads
+// owns one frame; in every pass thread t holds v[m] <-> element t + m*NT of that
+// pass's input.  A radix-R pass does E/R butterflies per thread; butterfly b uses
+// v[b + r*E/R], r < R.  Results go through a padded shared-memory exchange buffer
+// except after the last pass, whose outputs land in place (v[m] = Z[t + m*NT]).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace aa {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cmul_negi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+
+// exchange-buffer padding: one float2 every 16 keeps both the strided writes of the
+// first pass and the unit-stride reads at the ideal wavefront count.
+__host__ __device__ __forceinline__ constexpr int padidx(int i) { return i + (i >> 4); }
+__host__ __device__ constexpr int padded_len(int n) { return n + (n >> 4) + 1; }
+
+template <int R>
+struct Bfly;
+
+template <>
+struct Bfly<2> {
+    static __device__ __forceinline__ void run(float2 (&x)[2])
+    {
+        float2 a = x[0];
+        x[0] = cadd(a, x[1]);
+        x[1] = csub(a, x[1]);
+    }
+};
+
+template <>
+struct Bfly<4> {
+    static __device__ __forceinline__ void run(float2 (&x)[4])
+    {
+        float2 a0 = cadd(x[0], x[2]);
+        float2 a1 = csub(x[0], x[2]);
+        float2 a2 = cadd(x[1], x[3]);
+        float2 a3 = cmul_negi(csub(x[1], x[3]));
+        x[0] = cadd(a0, a2);
+        x[1] = cadd(a1, a3);
+        x[2] = csub(a0, a2);
+        x[3] = csub(a1, a3);
+    }
+};
+
+template <>
+struct Bfly<8> {
+    static __device__ __forceinline__ void run(float2 (&x)[8])
+    {
+        constexpr float C = 0.70710678118654752440f;
+        float2 e[4] = {x[0], x[2], x[4], x[6]};
+        float2 o[4] = {x[1], x[3], x[5], x[7]};
+        Bfly<4>::run(e);
+        Bfly<4>::run(o);
+        // o[k] *= exp(-2 pi i k / 8)
+        float2 o1 = make_float2(C * (o[1].x + o[1].y), C * (o[1].y - o[1].x));
+        float2 o2 = cmul_negi(o[2]);
+        float2 o3 = make_float2(C * (o[3].y - o[3].x), -C * (o[3].x + o[3].y));
+        x[0] = cadd(e[0], o[0]);
+        x[4] = csub(e[0], o[0]);
+        x[1] = cadd(e[1], o1);
+        x[5] = csub(e[1], o1);
+        x[2] = cadd(e[2], o2);
+        x[6] = csub(e[2], o2);
+        x[3] = cadd(e[3], o3);
+        x[7] = csub(e[3], o3);
+    }
+};
+
+template <>
+struct Bfly<16> {
+    static __device__ __forceinline__ void run(float2 (&x)[16])
+    {
+        constexpr float C = 0.70710678118654752440f;
+        constexpr float C1 = 0.92387953251128675613f;  // cos(pi/8)
+        constexpr float S1 = 0.38268343236508977173f;  // sin(pi/8)
+        float2 e[8] = {x[0], x[2], x[4], x[6], x[8], x[10], x[12], x[14]};
+        float2 o[8] = {x[1], x[3], x[5], x[7], x[9], x[11], x[13], x[15]};
+        Bfly<8>::run(e);
+        Bfly<8>::run(o);
+        // o[k] *= exp(-2 pi i k / 16) = (cos(k pi/8), -sin(k pi/8))
+        float2 w[8];
+        w[0] = o[0];
+        w[1] = cmul(o[1], make_float2(C1, -S1));
+        w[2] = make_float2(C * (o[2].x + o[2].y), C * (o[2].y - o[2].x));
+        w[3] = cmul(o[3], make_float2(S1, -C1));
+        w[4] = cmul_negi(o[4]);
+        w[5] = cmul(o[5], make_float2(-S1, -C1));
+        w[6] = make_float2(C * (o[6].y - o[6].x), -C * (o[6].x + o[6].y));
+        w[7] = cmul(o[7], make_float2(-C1, -S1));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x[k] = cadd(e[k], w[k]);
+            x[k + 8] = csub(e[k], w[k]);
+        }
+    }
+};
+
+// One Stockham pass.  NS = product of the radices already applied.  tw[i] =
+// exp(-2 pi i * i / N2).  If !LAST the butterfly outputs are scattered into `exch`
+// (padded indexing); the caller synchronises and reloads with fft_reload().
+template <int N2, int E, int R, int NS, bool LAST>
+__device__ __forceinline__ void fft_pass(float2 (&v)[E], int t, float2 *exch,
+                                         const float2 *__restrict__ tw)
+{
+    constexpr int NT = N2 / E;
+    constexpr int BPT = E / R;
+    static_assert(E % R == 0, "radix must divide the per-thread element count");
+#pragma unroll
+    for (int b = 0; b < BPT; ++b) {
+        const int j = t + b * NT;
+        float2 x[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r] = v[b + r * BPT];
+        const int k = j & (NS - 1);
+        if (NS > 1) {
+            constexpr int TSTEP = N2 / (NS * R);
+#pragma unroll
+            for (int r = 1; r < R; ++r) x[r] = cmul(x[r], __ldg(&tw[r * k * TSTEP]));
+        }
+        Bfly<R>::run(x);
+        if (LAST) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[b + r * BPT] = x[r];
+        } else {
+            const int j0 = (j / NS) * (NS * R) + k;
+#pragma unroll
+            for (int r = 0; r < R; ++r) exch[padidx(j0 + r * NS)] = x[r];
+        }
+    }
+}
+
+template <int N2, int E>
+__device__ __forceinline__ void fft_reload(float2 (&v)[E], int t, const float2 *exch)
+{
+    constexpr int NT = N2 / E;
+#pragma unroll
+    for (int m = 0; m < E; ++m) v[m] = exch[padidx(t + m * NT)];
+}
+
+// Per-window-size geometry: E complex elements per thread, NT = N/2/E threads.
+template <int N>
+struct Geo;
+template <>
+struct Geo<4096> { static constexpr int E = 16; };
+template <>
+struct Geo<2048> { static constexpr int E = 16; };
+template <>
+struct Geo<1024> { static constexpr int E = 8; };
+template <>
+struct Geo<512> { static constexpr int E = 8; };
+template <>
+struct Geo<256> { static constexpr int E = 4; };
+
+// Full N/2-point complex FFT of v (in: v[m] = z[t + m*NT]; out: v[m] = Z[t + m*NT]).
+// exA / exB: two padded exchange buffers of padded_len(N/2) float2 each.  Contains
+// the __syncthreads() calls between passes (all threads of the CTA must call it).
+template <int N>
+__device__ __forceinline__ void fft_half_complex(float2 (&v)[Geo<N>::E], int t, float2 *exA,
+                                                 float2 *exB, const float2 *__restrict__ tw)
+{
+    constexpr int N2 = N / 2;
+    constexpr int E = Geo<N>::E;
+    if constexpr (N == 4096) {              // 2048 = 16 * 16 * 8
+        fft_pass<N2, E, 16, 1, false>(v, t, exA, tw);
+        __syncthreads();
+        fft_reload<N2, E>(v, t, exA);
+        fft_pass<N2, E, 16, 16, false>(v, t, exB, tw);
+        __syncthreads();
+        fft_reload<N2, E>(v, t, exB);
+        fft_pass<N2, E, 8, 256, true>(v, t, nullptr, tw);
+    } else if constexpr (N == 2048) {       // 1024 = 16 * 16 * 4
+        fft_pass<N2, E, 16, 1, false>(v, t, exA, tw);
+        __syncthreads();
+        fft_reload<N2, E>(v, t, exA);
+        fft_pass<N2, E, 16, 16, false>(v, t, exB, tw);
+        __syncthreads();
+        fft_reload<N2, E>(v, t, exB);
+        fft_pass<N2, E, 4, 256, true>(v, t, nullptr, tw);
+    } else if constexpr (N == 1024) {       // 512 = 8 * 8 * 8
+        fft_pass<N2, E, 8, 1, false>(v, t, exA, tw);
+        __syncthreads();
+        fft_reload<N2, E>(v, t, exA);
+        fft_pass<N2, E, 8, 8, false>(v, t, exB, tw);
+        __syncthreads();
+        fft_reload<N2, E>(v, t, exB);
+        fft_pass<N2, E, 8, 64, true>(v, t, nullptr, tw);
+    } else if constexpr (N == 512) {        // 256 = 8 * 8 * 4
+        fft_pass<N2, E, 8, 1, false>(v, t, exA, tw);
+        __syncthreads();
+        fft_reload<N2, E>(v, t, exA);
+        fft_pass<N2, E, 8, 8, false>(v, t, exB, tw);
+        __syncthreads();
+        fft_reload<N2, E>(v, t, exB);
+        fft_pass<N2, E, 4, 64, true>(v, t, nullptr, tw);
+    } else {                                // N == 256: 128 = 4 * 4 * 4 * 2
+        static_assert(N == 256, "unsupported window size");
+        fft_pass<N2, E, 4, 1, false>(v, t, exA, tw);
+        __syncthreads();
+        fft_reload<N2, E>(v, t, exA);
+        fft_pass<N2, E, 4, 4, false>(v, t, exB, tw);
+        __syncthreads();
+        fft_reload<N2, E>(v, t, exB);
+        fft_pass<N2, E, 4, 16, false>(v, t, exA, tw);
+        __syncthreads();
+        fft_reload<N2, E>(v, t, exA);
+        fft_pass<N2, E, 2, 64, true>(v, t, nullptr, tw);
+    }
+}
+
+// realfft's split post-pass for one pair: a = Z[k], b = Z[N/2 - k], tw = 0.5*exp(-2 pi i k/N).
+// Produces X[k] (lo) and X[N/2 - k] (hi).  For k = 0 (b = Z[0], tw = (0.5, 0)) this yields
+// X[0] = (re+im, 0) and X[N/2] = (re-im, 0).
+__device__ __forceinline__ void rfft_postpass(float2 a, float2 b, float2 tw, float2 &lo, float2 &hi)
+{
+    const float sum_re = a.x + b.x, sum_im = a.y + b.y;
+    const float diff_re = a.x - b.x, diff_im = a.y - b.y;
+    const float half_sum_re = 0.5f * sum_re;
+    const float half_diff_im = 0.5f * diff_im;
+    const float otr = sum_im * tw.x + diff_re * tw.y;
+    const float oti = sum_im * tw.y - diff_re * tw.x;
+    lo = make_float2(half_sum_re + otr, half_diff_im + oti);
+    hi = make_float2(half_sum_re - otr, oti - half_diff_im);
+}
+
+}  // namespace aa

@@ -1,0 +1,156 @@
+// aa_fft_batch.cu -- batched real FFT kernels behind aa_fft_forward / aa_fft_inverse:
+// the FftProcessor::process_forward / process_inverse replacement
+// (reference src/dsp/fft.rs:33-41, 66-71, 96-101).
+//
+// One CTA transforms one frame at a time (grid-stride over the batch): coalesced float2
+// loads straight into the register-resident Stockham FFT of aa_fft.cuh, the realfft
+// split post-pass, coalesced float2 stores of the n/2+1 bins.
+#include "aa_fft.cuh"
+#include "aa_internal.h"
+
+namespace aa {
+
+template <int N>
+__global__ void __launch_bounds__(N / 2 / Geo<N>::E) fft_forward_kernel(const float *__restrict__ in,
+                                                                        int64_t batch,
+                                                                        float *__restrict__ out, Tables tab)
+{
+    constexpr int N2 = N / 2, E = Geo<N>::E, NT = N2 / E, EH = E / 2, HALF = N2 + 1, CBIN = N2 / 2;
+    constexpr int EXLEN = (padded_len(N2) + 1) & ~1;
+    __shared__ __align__(16) float2 exA[EXLEN];
+    __shared__ __align__(16) float2 exB[EXLEN];
+    const int t = threadIdx.x;
+
+    for (int64_t fr = blockIdx.x; fr < batch; fr += gridDim.x) {
+        const float2 *src = reinterpret_cast<const float2 *>(in + fr * N);
+        float2 v[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = __ldg(&src[t + m * NT]);
+        fft_half_complex<N>(v, t, exA, exB, tab.tw);
+
+        float2 *pbuf = (N == 256) ? exB : exA;
+#pragma unroll
+        for (int m = EH; m < E; ++m) pbuf[padidx(t + m * NT - CBIN)] = v[m];
+        if (t == 0) pbuf[padidx(CBIN)] = v[0];
+        __syncthreads();
+
+        float2 *dst = reinterpret_cast<float2 *>(out + fr * 2 * (int64_t)HALF);
+#pragma unroll
+        for (int m = 0; m < EH; ++m) {
+            const int k = t + m * NT;
+            const float2 b = pbuf[padidx(CBIN - k)];
+            float2 lo, hi;
+            rfft_postpass(v[m], b, __ldg(&tab.pt[k]), lo, hi);
+            if (k == 0) { lo.y = 0.0f; hi.y = 0.0f; }   // DC / Nyquist are purely real
+            dst[k] = lo;
+            dst[N2 - k] = hi;
+        }
+        if (t == 0) dst[CBIN] = make_float2(v[EH].x, -v[EH].y);
+        __syncthreads();   // pbuf / exchange buffers are reused by the next frame
+    }
+}
+
+// Inverse (complex -> real), realfft ComplexToReal semantics: unnormalised, i.e.
+// inverse(forward(x)) == n * x; the imaginary parts of bins 0 and n/2 are ignored.
+// Computed as conj(FFT(conj(Zin))) with Zin rebuilt from the half spectrum.
+template <int N>
+__global__ void __launch_bounds__(N / 2 / Geo<N>::E) fft_inverse_kernel(const float *__restrict__ spec,
+                                                                        int64_t batch,
+                                                                        float *__restrict__ out, Tables tab)
+{
+    constexpr int N2 = N / 2, E = Geo<N>::E, NT = N2 / E, HALF = N2 + 1;
+    constexpr int EXLEN = (padded_len(N2) + 1) & ~1;
+    __shared__ __align__(16) float2 exA[EXLEN];
+    __shared__ __align__(16) float2 exB[EXLEN];
+    const int t = threadIdx.x;
+
+    for (int64_t fr = blockIdx.x; fr < batch; fr += gridDim.x) {
+        const float2 *X = reinterpret_cast<const float2 *>(spec + fr * 2 * (int64_t)HALF);
+        float2 v[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            // z[k] = (X[k] + conj(X[N2-k])) + i * W^{-k} * (X[k] - conj(X[N2-k])),  W = exp(-2 pi i/N)
+            const int k = t + m * NT;
+            float2 a = __ldg(&X[k]);
+            float2 b = __ldg(&X[N2 - k]);
+            if (k == 0) { a.y = 0.0f; b.y = 0.0f; }
+            const float2 ev = make_float2(a.x + b.x, a.y - b.y);
+            const float2 od = make_float2(a.x - b.x, a.y + b.y);
+            // exp(+2 pi i k / N): from the post-pass table (0.5*exp(-2 pi i k/N)) for k < N/4, by symmetry above
+            float2 w;
+            if (k < N2 / 2) {
+                const float2 h = __ldg(&tab.pt[k]);
+                w = make_float2(2.0f * h.x, -2.0f * h.y);
+            } else if (k == N2 / 2) {
+                w = make_float2(0.0f, 1.0f);
+            } else {
+                const float2 h = __ldg(&tab.pt[N2 - k]);
+                w = make_float2(-2.0f * h.x, -2.0f * h.y);
+            }
+            const float2 iw = make_float2(-w.y, w.x);   // i * w
+            const float2 z = cadd(ev, cmul(iw, od));
+            v[m] = make_float2(z.x, -z.y);              // conj for the forward-FFT trick
+        }
+        fft_half_complex<N>(v, t, exA, exB, tab.tw);
+        float2 *dst = reinterpret_cast<float2 *>(out + fr * N);
+#pragma unroll
+        for (int m = 0; m < E; ++m) dst[t + m * NT] = make_float2(v[m].x, -v[m].y);
+        __syncthreads();
+    }
+}
+
+template <int N>
+static cudaError_t launch_fwd(const Tables &tab, const float *in, int64_t batch, float *out, int num_sms,
+                              cudaStream_t s)
+{
+    constexpr int NT = N / 2 / Geo<N>::E;
+    int per_sm = 2048 / NT;
+    if (per_sm > 16) per_sm = 16;
+    int64_t grid = (int64_t)num_sms * per_sm;
+    if (grid > batch) grid = batch;
+    fft_forward_kernel<N><<<(unsigned)grid, NT, 0, s>>>(in, batch, out, tab);
+    return cudaGetLastError();
+}
+
+template <int N>
+static cudaError_t launch_inv(const Tables &tab, const float *spec, int64_t batch, float *out, int num_sms,
+                              cudaStream_t s)
+{
+    constexpr int NT = N / 2 / Geo<N>::E;
+    int per_sm = 2048 / NT;
+    if (per_sm > 16) per_sm = 16;
+    int64_t grid = (int64_t)num_sms * per_sm;
+    if (grid > batch) grid = batch;
+    fft_inverse_kernel<N><<<(unsigned)grid, NT, 0, s>>>(spec, batch, out, tab);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fft_forward(int n, const Tables &tab, const float *in, int64_t batch, float *out,
+                               int num_sms, cudaStream_t s)
+{
+    if (batch <= 0) return cudaSuccess;
+    switch (n) {
+        case 4096: return launch_fwd<4096>(tab, in, batch, out, num_sms, s);
+        case 2048: return launch_fwd<2048>(tab, in, batch, out, num_sms, s);
+        case 1024: return launch_fwd<1024>(tab, in, batch, out, num_sms, s);
+        case 512: return launch_fwd<512>(tab, in, batch, out, num_sms, s);
+        case 256: return launch_fwd<256>(tab, in, batch, out, num_sms, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_fft_inverse(int n, const Tables &tab, const float *spec, int64_t batch, float *out,
+                               int num_sms, cudaStream_t s)
+{
+    if (batch <= 0) return cudaSuccess;
+    switch (n) {
+        case 4096: return launch_inv<4096>(tab, spec, batch, out, num_sms, s);
+        case 2048: return launch_inv<2048>(tab, spec, batch, out, num_sms, s);
+        case 1024: return launch_inv<1024>(tab, spec, batch, out, num_sms, s);
+        case 512: return launch_inv<512>(tab, spec, batch, out, num_sms, s);
+        case 256: return launch_inv<256>(tab, spec, batch, out, num_sms, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace aa

@@ -1,0 +1,60 @@
+// aa_internal.h -- shared between the kernel translation units and the C ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/aa_gpu.h"
+
+namespace aa {
+
+// Device tables built once per handle (host computes in f64 / with the reference's
+// own f32 formulas and uploads; see aa_api.cu::build_tables).
+struct Tables {
+    const float2 *tw;      // [n/2]   exp(-2 pi i k / (n/2))                complex-FFT twiddles
+    const float2 *pt;      // [n/4]   0.5 * exp(-2 pi i k / n)              realfft post-pass twiddles
+    const float2 *win2;    // [n/2]   (w[2m], w[2m+1]) periodic Hann, f32   stft.rs:641-648
+    const float  *flux_w;  // [n/2+1] 1 - k/half in f32                     onset.rs:280
+};
+
+// Persistent analyzer state of one clip / stream (used by the streaming API and by
+// serial chunk hand-off; batch mode passes nullptr and starts fresh).
+//   float bins[4][half]  : nfP (stft.rs:209), vol (:211), prev (:210 == onset.rs:149), nfO (onset.rs:175)
+//   float scalars[8]     : [0] FluxTracker.threshold, [1] energy_ema, [2] frames seen (as float),
+//                          [3] tracker track count
+//   float tracks[3][32]  : freq, score, life (as float)
+__host__ __device__ inline size_t state_floats(int half) { return (size_t)4 * half + 8 + 96; }
+
+struct AnalyzeParams {
+    const float *clips;
+    int64_t n_clips, clip_len, clip_stride, T;
+    const uint8_t *onset_in;
+    float *mags;
+    aa_frame_features *features;
+    aa_stable_pitches *stable;
+    float *dbg_floor;
+    uint8_t *dbg_peaks;
+    float *state;            // [n_clips][state_floats(half)] or nullptr
+    int64_t frame_base;      // streaming: index of the first frame (only affects nothing but bookkeeping)
+    Tables tab;
+    int n, hop, half;
+    float bin_width, min_freq, max_freq;
+    float global_floor;      // stft.rs:323-324
+    int min_bin, max_bin;    // stft.rs:454-455
+    uint32_t features_mask;
+};
+
+cudaError_t launch_analyze(const AnalyzeParams &p, cudaStream_t s);
+size_t      analyze_smem_bytes(int n);
+int         analyze_threads(int n);
+
+cudaError_t launch_fft_forward(int n, const Tables &tab, const float *in, int64_t batch, float *out,
+                               int num_sms, cudaStream_t s);
+cudaError_t launch_fft_inverse(int n, const Tables &tab, const float *spec, int64_t batch, float *out,
+                               int num_sms, cudaStream_t s);
+
+cudaError_t launch_summaries(const aa_frame_features *feat, int64_t n_clips, int64_t T,
+                             aa_clip_summary *out, cudaStream_t s);
+cudaError_t launch_synth(float *clips, int64_t n_clips, int64_t clip_len, int64_t clip_stride,
+                         float sample_rate, uint64_t seed, cudaStream_t s);
+
+}  // namespace aa

@@ -1,0 +1,144 @@
+// aa_misc.cu -- small support kernels: per-clip summaries (the multi-GPU gather payload)
+// and the synthetic-clip generator used by bench.py and the tests.
+#include "aa_internal.h"
+
+namespace aa {
+
+// ---------------------------------------------------------------------------
+// Per-clip summary: one warp per clip reduces that clip's feature records.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) summary_kernel(const aa_frame_features *__restrict__ feat,
+                                                      int64_t n_clips, int64_t T,
+                                                      aa_clip_summary *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t clip = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (clip >= n_clips) return;
+    const aa_frame_features *f = feat + clip * T;
+    unsigned n_pitched = 0, n_onsets = 0;
+    double s_top = 0.0, s_cent = 0.0, s_flux = 0.0, s_energy = 0.0;
+    float max_energy = 0.0f;
+    for (int64_t t = lane; t < T; t += 32) {
+        const aa_frame_features r = f[t];
+        if (r.n_pitches > 0) { ++n_pitched; s_top += (double)r.pitch[0].freq; }
+        if (r.flags & AA_FLAG_ONSET_DETECTED) ++n_onsets;
+        s_cent += (double)r.centroid;
+        s_flux += (double)r.flux;
+        s_energy += (double)r.energy;
+        max_energy = fmaxf(max_energy, r.energy);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_pitched += __shfl_xor_sync(0xffffffffu, n_pitched, o);
+        n_onsets += __shfl_xor_sync(0xffffffffu, n_onsets, o);
+        s_top += __shfl_xor_sync(0xffffffffu, s_top, o);
+        s_cent += __shfl_xor_sync(0xffffffffu, s_cent, o);
+        s_flux += __shfl_xor_sync(0xffffffffu, s_flux, o);
+        s_energy += __shfl_xor_sync(0xffffffffu, s_energy, o);
+        max_energy = fmaxf(max_energy, __shfl_xor_sync(0xffffffffu, max_energy, o));
+    }
+    if (lane == 0) {
+        aa_clip_summary s;
+        s.n_frames = (uint32_t)T;
+        s.n_pitched = n_pitched;
+        s.n_onsets = n_onsets;
+        s.mean_top_freq = n_pitched ? (float)(s_top / (double)n_pitched) : 0.0f;
+        s.mean_centroid = T ? (float)(s_cent / (double)T) : 0.0f;
+        s.mean_flux = T ? (float)(s_flux / (double)T) : 0.0f;
+        s.mean_energy = T ? (float)(s_energy / (double)T) : 0.0f;
+        s.max_energy = max_energy;
+        out[clip] = s;
+    }
+}
+
+cudaError_t launch_summaries(const aa_frame_features *feat, int64_t n_clips, int64_t T,
+                             aa_clip_summary *out, cudaStream_t s)
+{
+    if (n_clips <= 0) return cudaSuccess;
+    const int wpb = 4;
+    const unsigned grid = (unsigned)((n_clips + wpb - 1) / wpb);
+    summary_kernel<<<grid, wpb * 32, 0, s>>>(feat, n_clips, T, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Synthetic clips.
+// ---------------------------------------------------------------------------
+__host__ __device__ inline uint64_t splitmix64(uint64_t &x)
+{
+    uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ inline double u01(uint64_t r) { return (double)(r >> 11) * (1.0 / 9007199254740992.0); }
+
+struct ClipVoice {
+    int k;
+    double f_over_sr[4];   // f0 / sample_rate
+    float amp[4];
+    float phase[4][6];     // in turns
+};
+
+__device__ inline ClipVoice make_voice(uint64_t seed, int64_t clip, float sample_rate)
+{
+    uint64_t st = seed + (uint64_t)clip;
+    ClipVoice v;
+    v.k = 1 + (int)(splitmix64(st) & 3ull);
+    const double a_total = 0.05 + 0.45 * u01(splitmix64(st));
+    for (int i = 0; i < 4; ++i) {
+        const double lf = log(55.0) + (log(1760.0) - log(55.0)) * u01(splitmix64(st));
+        v.f_over_sr[i] = exp(lf) / (double)sample_rate;
+        v.amp[i] = (float)(a_total / (double)v.k);
+        for (int h = 0; h < 6; ++h) v.phase[i][h] = (float)u01(splitmix64(st));
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256) synth_kernel(float *__restrict__ clips, int64_t n_clips, int64_t clip_len,
+                                                    int64_t clip_stride, float sample_rate, uint64_t seed)
+{
+    const int64_t clip = blockIdx.y;
+    if (clip >= n_clips) return;
+    const ClipVoice v = make_voice(seed, clip, sample_rate);
+    float *dst = clips + clip * clip_stride;
+    const float noise_amp = 1.0e-3f * 1.7320508f;   // uniform with RMS 1e-3 (-60 dBFS)
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < clip_len;
+         n += (int64_t)gridDim.x * blockDim.x) {
+        float acc = 0.0f;
+        for (int i = 0; i < v.k; ++i) {
+            const double base = v.f_over_sr[i] * (double)n;
+#pragma unroll
+            for (int h = 1; h <= 6; ++h) {
+                if (v.f_over_sr[i] * h < 0.5) {
+                    double ph = base * (double)h;
+                    ph -= floor(ph);
+                    acc += (v.amp[i] / (float)h) * sinpif(2.0f * ((float)ph + v.phase[i][h - 1]));
+                }
+            }
+        }
+        uint64_t st = seed * 0x2545F4914F6CDD1Dull + (uint64_t)clip * 0x9E3779B97F4A7C15ull + (uint64_t)n;
+        const float u = (float)u01(splitmix64(st)) * 2.0f - 1.0f;
+        dst[n] = acc + noise_amp * u;
+    }
+}
+
+cudaError_t launch_synth(float *clips, int64_t n_clips, int64_t clip_len, int64_t clip_stride,
+                         float sample_rate, uint64_t seed, cudaStream_t s)
+{
+    if (n_clips <= 0 || clip_len <= 0) return cudaSuccess;
+    int64_t bx = (clip_len + 255) / 256;
+    if (bx > 64) bx = 64;
+    // grid.y is limited to 65535: loop in slabs
+    for (int64_t c0 = 0; c0 < n_clips; c0 += 65535) {
+        const int64_t nc = (n_clips - c0) < 65535 ? (n_clips - c0) : 65535;
+        dim3 grid((unsigned)bx, (unsigned)nc);
+        synth_kernel<<<grid, 256, 0, s>>>(clips + c0 * clip_stride, nc, clip_len, clip_stride, sample_rate,
+                                          seed + (uint64_t)c0);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace aa

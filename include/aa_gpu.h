@@ -1,0 +1,218 @@
+/*
+ * aa_gpu.h -- C ABI of libaa_gpu.so: the B200 (sm_100a) implementation of
+ * audio-analyzer-rs's frame-analysis hot path.
+ *
+ * This is the drop-in boundary.  The reference (a Rust crate, paths below are
+ * relative to its root) has no FFI of its own on this path; each entry point
+ * here names the Rust item it replaces, and INTEGRATION.md shows the Rust
+ * `extern "C"` binding a maintainer would add.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no C++ or torch types.
+ *   - Every call returns aa_status: 0 = AA_OK, < 0 = error.  The library never
+ *     aborts; aa_last_error() returns a thread-local message for the last
+ *     failing call (the reference panics via unwrap() instead, fft.rs:69,99).
+ *   - A handle is single-threaded (the reference's `&mut self` contract);
+ *     distinct handles may be used concurrently from distinct threads.
+ *   - `stream` arguments are a cudaStream_t passed as void* (NULL = the
+ *     handle's own stream).  *_device entry points are asynchronous on that
+ *     stream; *_host entry points return when the results are in host memory.
+ *   - There is no CPU fallback: with no usable sm_100 device every create call
+ *     fails with AA_ERR_NO_DEVICE.
+ */
+#ifndef AA_GPU_H
+#define AA_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define AA_API __declspec(dllexport)
+#else
+#define AA_API __attribute__((visibility("default")))
+#endif
+
+typedef int32_t aa_status;
+#define AA_OK               0
+#define AA_ERR_INVALID     -1   /* bad argument (length mismatch, null pointer, ...)      */
+#define AA_ERR_UNSUPPORTED -2   /* geometry the kernels are not built for                  */
+#define AA_ERR_NO_DEVICE   -3   /* no CUDA device / not sm_100                             */
+#define AA_ERR_CUDA        -4   /* CUDA runtime error, text in aa_last_error()             */
+#define AA_ERR_OVERFLOW    -5   /* streaming ring overrun / output array too small         */
+
+AA_API const char *aa_last_error(void);
+AA_API int32_t     aa_version(void);                     /* 10000*major + 100*minor + patch */
+AA_API aa_status   aa_device_count(int32_t *count);
+AA_API aa_status   aa_set_device(int32_t device);        /* device used by subsequently created handles */
+
+/* pinned host memory for the *_host entry points (pageable memory also works, slower) */
+AA_API aa_status aa_host_alloc(size_t bytes, void **out);
+AA_API aa_status aa_host_free(void *p);
+AA_API aa_status aa_device_alloc(size_t bytes, void **out);
+AA_API aa_status aa_device_free(void *p);
+AA_API aa_status aa_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes);
+AA_API aa_status aa_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
+AA_API aa_status aa_device_synchronize(void);
+
+/* ------------------------------------------------------------------------- *
+ * FftProcessor  (src/dsp/fft.rs:6-41)
+ *   FftProcessor::new(len)                      -> aa_fft_create
+ *   process_forward(&mut self, &mut [f32])      -> aa_fft_forward      (fft.rs:33)
+ *   process_inverse(&mut self, &mut [Complex])  -> aa_fft_inverse      (fft.rs:39)
+ * Spectra are n/2+1 interleaved (re,im) f32 pairs, unnormalised, as realfft
+ * returns them.  `batch` frames are transformed per call (the reference does
+ * one); frame b starts at in + b*n and its spectrum at out + b*2*(n/2+1).
+ * Unlike the reference the input is not clobbered.
+ * ------------------------------------------------------------------------- */
+typedef struct aa_fft aa_fft;
+AA_API aa_status aa_fft_create(int32_t n, aa_fft **out);            /* n in {256,512,1024,2048,4096} */
+AA_API aa_status aa_fft_destroy(aa_fft *h);
+AA_API int32_t   aa_fft_len(const aa_fft *h);
+AA_API aa_status aa_fft_forward(aa_fft *h, const float *in_host, int64_t batch, float *out_host);
+AA_API aa_status aa_fft_forward_device(aa_fft *h, const float *in_dev, int64_t batch,
+                                       float *out_dev, void *stream);
+AA_API aa_status aa_fft_inverse(aa_fft *h, const float *spec_host, int64_t batch, float *out_host);
+AA_API aa_status aa_fft_inverse_device(aa_fft *h, const float *spec_dev, int64_t batch,
+                                       float *out_dev, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Frame analysis: the bodies of STFT::detect_pitches (src/audio_io/stft.rs:
+ * 273-438) and OnsetDetector::detect_onsets (src/analysis/onset.rs:244-357).
+ * ------------------------------------------------------------------------- */
+#define AA_FEAT_PITCH    1u  /* stft.rs:320-381  adaptive floor + extract_pitches (:443-620) */
+#define AA_FEAT_ONSET    2u  /* onset.rs:261-357 flux / burst floor / EMA / FluxTracker      */
+#define AA_FEAT_CENTROID 4u  /* NEW (no reference): spectral centroid in Hz                  */
+#define AA_FEAT_TRACKER  8u  /* stft.rs:45-116   PitchTracker hysteresis (needs PITCH)       */
+#define AA_FEAT_ALL      15u
+
+#define AA_FLAG_FLUX_ONSET     1u   /* FluxTracker::update() == true       onset.rs:355 */
+#define AA_FLAG_BURST_ONSET    2u   /* max_excess > 3 && burst_count >= 3  onset.rs:356 */
+#define AA_FLAG_ONSET_DETECTED 4u   /* both                                onset.rs:357 */
+#define AA_FLAG_ENERGY_RISING  8u   /* energy > 1.5 * energy_ema           onset.rs:373 */
+
+#define AA_MAX_NOTES   8    /* stft.rs:452 MAX_NOTES */
+#define AA_MAX_STABLE 16    /* bound on displayed PitchTracker tracks */
+
+typedef struct aa_config {
+    int32_t  n;               /* window: 256,512,1024,2048,4096 (stft.rs:170 = 2048, onset.rs:122 = 256) */
+    int32_t  hop;             /* hop: n/4 (stft.rs:169, onset.rs:123), also n/2 and n/8 accepted         */
+    float    sample_rate;     /* `sr` argument of detect_pitches (stft.rs:160)                           */
+    float    min_freq;        /* MIN_FREQ = 24.0     (stft.rs:173) */
+    float    max_freq;        /* MAX_FREQ = 10000.0  (stft.rs:174) */
+    float    noise_floor_db;  /* DynamicsOutput.noise_floor_db, default -96 (dynamics.rs:93-103)         */
+    uint32_t features;        /* AA_FEAT_* */
+} aa_config;
+
+AA_API void aa_config_default_pitch(aa_config *cfg, float sample_rate);  /* 2048/512, PITCH|TRACKER      */
+AA_API void aa_config_default_onset(aa_config *cfg, float sample_rate);  /* 256/64,   ONSET              */
+
+/* One record per frame, 96 bytes. */
+typedef struct aa_pitch { float freq, score; } aa_pitch;
+typedef struct aa_frame_features {
+    uint32_t n_pitches;                 /* raw pitches of extract_pitches, <= 8               */
+    aa_pitch pitch[AA_MAX_NOTES];       /* (Hz, score), descending score                      */
+    float    flux;                      /* onset.rs:261-291, zeroed when burst_count < 2      */
+    float    energy;                    /* onset.rs:276 sum of magnitudes                     */
+    float    centroid;                  /* Hz                                                 */
+    uint32_t burst_count;               /* onset.rs:312-319                                   */
+    float    max_excess;                /* onset.rs:329-331                                   */
+    uint32_t flags;                     /* AA_FLAG_*                                          */
+    float    energy_ema;                /* onset.rs:350 after this frame                      */
+} aa_frame_features;
+
+/* PitchTracker::process output (stft.rs:45-116), 136 bytes; what `note_tx` carries (stft.rs:431-434). */
+typedef struct aa_stable_pitches {
+    uint32_t n;
+    uint32_t reserved;
+    aa_pitch pitch[AA_MAX_STABLE];
+} aa_stable_pitches;
+
+/* Per-clip summary (NEW; the payload of the multi-GPU gather), 32 bytes. */
+typedef struct aa_clip_summary {
+    uint32_t n_frames;
+    uint32_t n_pitched;        /* frames with n_pitches > 0                      */
+    uint32_t n_onsets;         /* frames with AA_FLAG_ONSET_DETECTED             */
+    float    mean_top_freq;    /* mean of pitch[0].freq over pitched frames, Hz  */
+    float    mean_centroid;
+    float    mean_flux;
+    float    mean_energy;
+    float    max_energy;
+} aa_clip_summary;
+
+/* Output arrays; any pointer may be NULL (= not produced).  Device pointers for
+ * aa_analyze_device, host pointers for aa_analyze_host.  Frames of clip c are at
+ * index c*T + t with T = aa_num_frames(clip_len). */
+typedef struct aa_outputs {
+    float             *mags;       /* [n_clips*T][n/2+1] magnitude spectra (stft.rs:314-318) */
+    aa_frame_features *features;   /* [n_clips*T]                                           */
+    aa_stable_pitches *stable;     /* [n_clips*T]                                           */
+    aa_clip_summary   *summaries;  /* [n_clips]  (needs `features`)                         */
+    /* parity-test taps, NULL in production */
+    float             *dbg_floor;  /* [n_clips*T][n/2+1] effective pitch floor (stft.rs:365-367) */
+    uint8_t           *dbg_peaks;  /* [n_clips*T][n/2+1] is_peak (stft.rs:461-469)               */
+} aa_outputs;
+
+typedef struct aa_analyzer aa_analyzer;
+AA_API aa_status aa_analyzer_create(const aa_config *cfg, aa_analyzer **out);
+AA_API aa_status aa_analyzer_destroy(aa_analyzer *h);
+/* T = (clip_len - n)/hop + 1, 0 if clip_len < n: frame t covers samples [t*hop, t*hop+n),
+ * the offline reading of `while available_samples >= window_size` (stft.rs:273,436). */
+AA_API int64_t   aa_num_frames(const aa_config *cfg, int64_t clip_len);
+
+/* clips_dev: n_clips clips, clip c starting at clips_dev + c*clip_stride (samples,
+ * multiple of 4; clips may overlap, which is how hop-aligned chunks of a long stream
+ * with a window halo are expressed).  Analyzer state (floors, trackers) starts fresh
+ * for every clip.  onset_in_dev (optional, [n_clips*T] bytes) is PitchTracker's
+ * `onset` argument per frame (the reference's onset_pending flag, stft.rs:387). */
+AA_API aa_status aa_analyze_device(aa_analyzer *h, const float *clips_dev, int64_t n_clips,
+                                   int64_t clip_len, int64_t clip_stride,
+                                   const uint8_t *onset_in_dev, const aa_outputs *out_dev,
+                                   void *stream);
+/* Same, host buffers: H2D, kernels and D2H are pipelined over clip groups. */
+AA_API aa_status aa_analyze_host(aa_analyzer *h, const float *clips_host, int64_t n_clips,
+                                 int64_t clip_len, int64_t clip_stride,
+                                 const uint8_t *onset_in_host, const aa_outputs *out_host);
+/* Number of kernel launches issued by the last aa_analyze_* call on this handle. */
+AA_API int64_t   aa_analyzer_last_launches(const aa_analyzer *h);
+
+/* ------------------------------------------------------------------------- *
+ * Streaming: the thread body of STFT::detect_pitches / OnsetDetector::
+ * detect_onsets with the SlotPool -> private ring hand-off (stft.rs:240-266,
+ * onset.rs:216-237, audio_io/mod.rs:32-79) replaced by a pinned-host +
+ * device ring.  The Rust worker thread stays; its body becomes push / poll.
+ * ------------------------------------------------------------------------- */
+typedef struct aa_stream aa_stream;
+typedef struct aa_stream_frame {
+    int64_t           frame_index;     /* frames since stream creation                 */
+    aa_frame_features features;
+    aa_stable_pitches stable;
+} aa_stream_frame;
+
+AA_API aa_status aa_stream_create(const aa_config *cfg, aa_stream **out);
+AA_API aa_status aa_stream_destroy(aa_stream *h);
+/* Append `count` mono f32 samples (one 1024-sample slot in the reference, mod.rs:126-128;
+ * any count <= ring capacity here) and run every frame that became complete. */
+AA_API aa_status aa_stream_push(aa_stream *h, const float *samples, int32_t count);
+AA_API aa_status aa_stream_set_noise_floor_db(aa_stream *h, float db);   /* stft.rs:322 */
+AA_API aa_status aa_stream_signal_onset(aa_stream *h);                   /* onset_pending, stft.rs:387 */
+/* Copy up to `max` completed frames (oldest first); *n_out receives the count. */
+AA_API aa_status aa_stream_poll(aa_stream *h, aa_stream_frame *out, int32_t max, int32_t *n_out);
+AA_API aa_status aa_stream_reset(aa_stream *h);
+
+/* ------------------------------------------------------------------------- *
+ * Synthetic clips (bench/test support): clip c = K = 1..4 harmonic
+ * tones (6 partials, 1/h amplitudes, f0 log-uniform in [55,1760] Hz) plus white
+ * noise at -60 dBFS, all derived from splitmix64(seed + c).
+ * ------------------------------------------------------------------------- */
+AA_API aa_status aa_synth_clips_device(float *clips_dev, int64_t n_clips, int64_t clip_len,
+                                       int64_t clip_stride, float sample_rate, uint64_t seed,
+                                       void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AA_GPU_H */

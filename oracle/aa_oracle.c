@@ -334,11 +334,13 @@ static inline size_t f32_as_usize(float x)
     return (size_t)x;
 }
 
-static inline void margin_update(float *m, float dist)
+static int g_margin_src_dummy;
+static inline void margin_update2(float *m, int *src, float dist, int tag)
 {
     if (dist < 0.0f) dist = -dist;
-    if (dist < *m) *m = dist;
+    if (dist < *m) { *m = dist; *src = tag; }
 }
+#define margin_update(m, dist, tag) margin_update2((m), &margin_src, (dist), (tag))
 
 typedef struct { int bin; float score; } aao_cand;
 
@@ -348,6 +350,8 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
 {
     enum { MAX_HARMONICS = 14, MAX_NOTES = 8 };                     /* :451-452 */
     float margin = 1.0f;
+    int margin_src = 0;
+    (void)g_margin_src_dummy;
     if (diag) {
         memset(diag, 0, sizeof(*diag));
         diag->min_margin = 1.0f;
@@ -388,6 +392,7 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
         }
         ++n_scored;
         float frac_bin;
+        int frac_is_exact = 0;
         if (k >= 1 && k + 1 < half_size) {                           /* :484-494 */
             float y_l = logf(magnitudes[k - 1]);
             float y_c = logf(magnitudes[k]);
@@ -395,7 +400,14 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
             float denom = y_l - 2.0f * y_c + y_r;
             float delta;
             if (fabsf(denom) < 1e-30f) delta = 0.0f;
-            else delta = clampf(0.5f * (y_l - y_r) / denom, -1.0f, 1.0f);
+            else {
+                float raw = 0.5f * (y_l - y_r) / denom;
+                delta = clampf(raw, -1.0f, 1.0f);
+                /* a robustly clamped delta is an exact +-1: frac_bin is then an integer in
+                 * every implementation and the comb-window boundaries carry no rounding risk */
+                frac_is_exact = fabsf(raw) > 1.001f;
+                if (!frac_is_exact) margin_update(&margin, fabsf(raw) - 1.0f, 11);
+            }
             frac_bin = (float)k + delta;
         } else {
             frac_bin = (float)k;
@@ -406,12 +418,12 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
         int longest_run = 0, current_run = 0, total_harms = 0;
         for (int n = 2; n <= MAX_HARMONICS; ++n) {                   /* :504 */
             float expected_f = frac_bin * (float)n;                  /* :505 */
-            margin_update(&margin, (expected_f - (float)half_size) / (float)half_size);
+            if (!frac_is_exact) margin_update(&margin, (expected_f - (float)half_size) / (float)n, 1);
             if (expected_f >= (float)half_size) break;               /* :506-508 */
-            {   /* distance of expected_f from the nearest integer, relative */
+            if (!frac_is_exact) {   /* distance of expected_f from the nearest integer, relative */
                 float r = expected_f - floorf(expected_f);
                 float d = r < 0.5f ? r : 1.0f - r;
-                margin_update(&margin, d / fmaxf(expected_f, 1.0f));
+                margin_update(&margin, d / (float)n, 2);   /* frac_bin perturbation that flips it */
             }
             size_t search_start = f32_as_usize(floorf(expected_f - 1.0f));   /* :509 */
             if (search_start < last + 1) search_start = last + 1;
@@ -462,7 +474,7 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
         int nc = 0;
         for (int pi = 0; pi < n_peaks; ++pi) {                       /* :553-562 */
             int k = peak_bins[pi];
-            if (scores[k] != 0.0f) margin_update(&margin, (scores[k] - cutoff) / cutoff);
+            if (scores[k] != 0.0f) margin_update(&margin, (scores[k] - cutoff) / cutoff, 3);
             if (scores[k] >= cutoff) { cand[nc].bin = k; cand[nc].score = scores[k]; ++nc; }
         }
         if (diag) diag->n_candidates = nc;
@@ -480,12 +492,12 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
                 {   /* margins: ratio near x.5, |ratio/nearest-1| near 0.03, score test */
                     float fr = ratio - floorf(ratio);
                     if (ratio > 1.4f && ratio < 5.6f) {
-                        margin_update(&margin, fr - 0.5f);
+                        margin_update(&margin, fr - 0.5f, 4);
                         if (nearest >= 2.0f && nearest <= 5.0f) {
                             float dev = fabsf(ratio / nearest - 1.0f);
-                            margin_update(&margin, (dev - 0.03f) / 0.03f);
+                            margin_update(&margin, (dev - 0.03f) / 0.03f, 5);
                             if (dev < 0.03f)
-                                margin_update(&margin, (score_i - score_j * 1.05f) / score_i);
+                                margin_update(&margin, (score_i - score_j * 1.05f) / score_i, 6);
                         }
                     }
                 }
@@ -512,7 +524,7 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
             cand[j + 1] = c;
         }
         for (int i = 1; i < nk; ++i)
-            margin_update(&margin, (cand[i - 1].score - cand[i].score) / cand[i - 1].score);
+            margin_update(&margin, (cand[i - 1].score - cand[i].score) / cand[i - 1].score, 7);
 
         const float MIN_BIN_SEPARATION = 2.0f;                       /* :594-605 */
         int nd = 0;
@@ -521,7 +533,7 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
             int conflict = 0;
             for (int j = 0; j < nd; ++j) {
                 float d = fabsf(frac_i - frac_bins[cand[j].bin]);
-                margin_update(&margin, (d - MIN_BIN_SEPARATION) / MIN_BIN_SEPARATION);
+                margin_update(&margin, (d - MIN_BIN_SEPARATION) / MIN_BIN_SEPARATION, 8);
                 if (d < MIN_BIN_SEPARATION) { conflict = 1; break; }
             }
             if (!conflict) cand[nd++] = cand[i];
@@ -530,8 +542,8 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
 
         for (int i = 0; i < nd; ++i) {                               /* :608-619 */
             float freq = frac_bins[cand[i].bin] * bin_width;
-            margin_update(&margin, (freq - min_freq) / min_freq);
-            margin_update(&margin, (freq - max_freq) / max_freq);
+            margin_update(&margin, (freq - min_freq) / min_freq, 9);
+            margin_update(&margin, (freq - max_freq) / max_freq, 10);
             if (freq >= min_freq && freq <= max_freq) {
                 out_pairs[2 * n_out] = freq;
                 out_pairs[2 * n_out + 1] = cand[i].score;
@@ -542,7 +554,7 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
         free(cand);
     }
 done:
-    if (diag) { diag->n_out = n_out; diag->min_margin = margin; }
+    if (diag) { diag->n_out = n_out; diag->min_margin = margin; diag->margin_src = margin_src; }
     free(is_peak); free(peak_bins); free(scores); free(frac_bins);
     return n_out;
 }

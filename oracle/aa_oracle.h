@@ -81,11 +81,15 @@ typedef struct aao_pitch_diag {
     int32_t  n_candidates;       /* after the 0.5*max cutoff            stft.rs:553-562 */
     int32_t  n_out;              /* returned pitches                                    */
     int32_t  out_bins[AAO_MAX_NOTES];   /* integer bin of each returned pitch           */
-    /* Smallest relative distance of any float-derived discrete decision from its
-     * flip point (comb-window integer boundaries, cutoff, ghost test, sort order,
-     * dedup distance, frequency range).  Decisions on raw magnitudes are exact
-     * given identical magnitudes and are not included.  */
+    /* Smallest perturbation that would flip any discrete decision taken on a
+     * transcendental-derived float: in units of frac_bin for the comb-window integer
+     * boundaries (classes 1, 2, 11), relative for scores / ratios / frequencies
+     * (cutoff 3, ghost test 4-6, sort order 7, dedup 8, range 9-10).  libm logf/log2f
+     * and CUDA logf/log2f may differ by 1 ulp, so frames with min_margin below ~1e-5
+     * are the documented near-ties.  Decisions on raw magnitudes are exact given
+     * identical magnitudes and are not included.  */
     float    min_margin;
+    int32_t  margin_src;         /* which decision class produced min_margin (1..10, aa_oracle.c) */
 } aao_pitch_diag;
 
 /* ---- a1: window (stft.rs:641-648 == onset.rs:549-556) ------------------------- */

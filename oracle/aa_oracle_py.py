@@ -51,9 +51,10 @@ DIAG_DTYPE = np.dtype(
         ("n_out", "<i4"),
         ("out_bins", "<i4", (MAX_NOTES,)),
         ("min_margin", "<f4"),
+        ("margin_src", "<i4"),
     ]
 )
-assert DIAG_DTYPE.itemsize == 52
+assert DIAG_DTYPE.itemsize == 56
 
 
 class Config(C.Structure):
