@@ -1,0 +1,282 @@
+"""GPU parity of the fused frame-analysis kernel (aa_analyze_*) against the oracle.
+
+Two kinds of checks (DESIGN.md "Parity"):
+  end-to-end      signal -> GPU  vs  signal -> oracle: spectra within 1e-4 of the frame maximum
+                  (north_star tolerance); discrete outputs equal except documented near-ties.
+  stage-isolated  the GPU's own magnitudes fed to the oracle's feature stage: the recurrences use
+                  the same op-by-op f32 arithmetic, so floors, peak masks, burst counts and
+                  max_excess are BIT-EXACT; log-derived floats agree to ~1 ulp; pitch lists are
+                  identical unless the oracle itself flags the frame as a near-tie.
+"""
+import numpy as np
+import pytest
+
+import signals
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(aa, clips, n, sr, features=15, db=-96.0, onset_in=None, dbg=True):
+    an = aa.Analyzer(aa.Config(n=n, sample_rate=sr, noise_floor_db=db, features=features))
+    res = an.analyze_host(np.atleast_2d(clips), want_dbg=dbg, onset_in=onset_in)
+    res["launches"] = an.last_launches
+    return res
+
+
+def check_stage_isolated(O, res, c, n, sr, db=-96.0, features=15, onset_in=None, label=""):
+    """Feed the GPU magnitudes of clip c through the oracle feature stage and compare."""
+    cfg = O.make_config(n, n // 4, sr, noise_floor_db=db, features=features)
+    iso = O.analyze_clip(cfg, mags_in=res["mags"][c], onset_in=onset_in, want_floor=True, want_peaks=True,
+                         want_diag=True)
+    g, o = res["features"][c], iso["features"]
+    T = iso["T"]
+    if features & 1:
+        assert np.array_equal(res["dbg_floor"][c], iso["floor"]), f"{label}: pitch floor not bit-exact"
+        assert np.array_equal(res["dbg_peaks"][c], iso["peaks"]), f"{label}: peak mask differs"
+        bad, ties = util.compare_pitch_records(g, o, iso["diag"])
+        assert len(bad) == 0, f"{label}: pitch lists differ on non-tie frames {bad[:10]}"
+        assert len(ties) <= max(2, 0.05 * T), f"{label}: too many near-tie mismatches {len(ties)}/{T}"
+        if features & 8:
+            ok_frames = np.ones(T, bool)
+            if len(ties):
+                ok_frames[ties.min():] = False      # a tie perturbs the tracker from there on
+            badst = util.compare_stable(res["stable"][c][ok_frames], iso["stable"][ok_frames])
+            assert len(badst) == 0, f"{label}: PitchTracker output differs at {badst[:10]}"
+    if features & 2:
+        assert np.array_equal(g["burst_count"], o["burst_count"]), f"{label}: burst_count"
+        assert np.array_equal(g["max_excess"], o["max_excess"]), f"{label}: max_excess not bit-exact"
+        assert util.ulp_close(g["energy"], o["energy"], 1e-5).all(), f"{label}: energy"
+        assert util.ulp_close(g["flux"], o["flux"], 2e-5, 1e-6).all(), f"{label}: flux"
+        assert util.ulp_close(g["energy_ema"], o["energy_ema"], 1e-5).all(), f"{label}: ema"
+        nflag = int((g["flags"] != o["flags"]).sum())
+        assert nflag <= max(1, 0.01 * T), f"{label}: {nflag} onset-flag mismatches"
+    if features & 4:
+        assert util.ulp_close(g["centroid"], o["centroid"], 1e-5, 1e-3).all(), f"{label}: centroid"
+    return iso
+
+
+@pytest.mark.parametrize("path", util.golden_files(), ids=lambda p: p.split("/")[-1][:-4])
+def test_golden_fixtures(aa, O, torch_cuda, path):
+    g = util.load_golden(path)
+    res = run_gpu(aa, g["samples"], g["n"], g["sr"], db=g["db"], onset_in=g["onset_in"])
+    assert res["T"] == g["mags"].shape[0]
+    err = util.mag_err(res["mags"][0], g["mags"])
+    assert err.max() <= util.MAG_TOL, err.max()
+    assert err.max() <= 2e-6            # what the kernel actually achieves against float64
+    check_stage_isolated(O, res, 0, g["n"], g["sr"], g["db"], onset_in=g["onset_in"], label=path[-24:])
+    # end to end against the golden records: equal wherever the golden frame is not a near-tie
+    same = res["features"][0]["n_pitches"] == g["n_pitches"]
+    assert same.mean() > 0.9
+    assert np.array_equal(res["features"][0]["burst_count"], g["ints"][:, 0]) or \
+        (res["features"][0]["burst_count"] != g["ints"][:, 0]).mean() < 0.02
+
+
+def test_cfg1_sine_440(aa, O, torch_cuda):
+    """BASELINE configs[0]: 440 Hz sine, 44.1 kHz mono 10 s, 2048-pt Hann STFT hop 512 + pitch."""
+    x = signals.sine(440.0, 44100.0, 441000)
+    res = run_gpu(aa, x, 2048, 44100.0)
+    assert res["T"] == 858
+    ref = O.analyze_clip(O.make_config(2048, 512, 44100.0), x)
+    assert util.mag_err(res["mags"][0], ref["mags"]).max() <= util.MAG_TOL
+    assert (res["mags"][0].argmax(axis=1) == 20).all()
+    f = res["features"][0]
+    assert (f["n_pitches"] == 1).all()
+    assert np.allclose(f["pitch"]["freq"][:, 0], 440.196, atol=2e-3)
+    assert np.allclose(f["pitch"]["score"][:300, 0], 0.522, atol=1e-3)
+    st = res["stable"][0]
+    assert st["n"][0] == 0 and (st["n"][1:] == 1).all()
+    check_stage_isolated(O, res, 0, 2048, 44100.0, label="cfg1")
+
+
+@pytest.mark.parametrize("n,sr", [(256, 48000.0), (512, 22050.0), (1024, 48000.0), (2048, 44100.0),
+                                  (4096, 48000.0), (4096, 16000.0)])
+def test_all_window_sizes_multiclip(aa, O, torch_cuda, n, sr):
+    clips = np.stack([signals.multitone(100 + i, sr, 10 * n + 3 * (n // 4)) for i in range(5)]
+                     + [signals.note_sequence(7, sr, 10 * n + 3 * (n // 4))])
+    res = run_gpu(aa, clips, n, sr)
+    cfg = O.make_config(n, n // 4, sr)
+    for c in range(clips.shape[0]):
+        ref = O.analyze_clip(cfg, clips[c])
+        assert util.mag_err(res["mags"][c], ref["mags"]).max() <= 2e-6
+        check_stage_isolated(O, res, c, n, sr, label=f"n={n} clip {c}")
+
+
+@pytest.mark.parametrize("features", [0, 1, 2, 4, 1 | 8, 2 | 4, 1 | 2, 15])
+def test_feature_subsets(aa, O, torch_cuda, features):
+    x = np.stack([signals.multitone(3, 44100.0, 30000), signals.note_sequence(4, 44100.0, 30000)])
+    res = run_gpu(aa, x, 2048, 44100.0, features=features)
+    full = run_gpu(aa, x, 2048, 44100.0, features=15)
+    assert np.array_equal(res["mags"], full["mags"])
+    cfg = O.make_config(2048, 512, 44100.0, features=features)
+    for c in range(2):
+        check_stage_isolated(O, res, c, 2048, 44100.0, features=features, label=f"features={features}")
+        ref = O.analyze_clip(cfg, mags_in=res["mags"][c])
+        if not features & 1:
+            assert (res["features"][c]["n_pitches"] == 0).all() and (res["stable"][c]["n"] == 0).all()
+        if not features & 2:
+            assert (res["features"][c]["flux"] == 0).all() and (res["features"][c]["flags"] == 0).all()
+        if not features & 4:
+            assert (res["features"][c]["centroid"] == 0).all()
+        if not features & 8:
+            assert (res["stable"][c]["n"] == 0).all()
+
+
+def test_edge_lengths_and_silence(aa, O, torch_cuda):
+    n, sr = 1024, 48000.0
+    an = aa.Analyzer(aa.Config(n=n, sample_rate=sr))
+    # shorter than one window -> zero frames, no launch
+    r = an.analyze_host(np.zeros((3, n - 4), np.float32))
+    assert r["T"] == 0 and an.last_launches == 0
+    # exactly one window / ragged tails that do not fill a hop
+    for extra in (0, 4, 252, 256, 260):
+        x = signals.multitone(9, sr, n + extra)[None, :]
+        r = an.analyze_host(x)
+        assert r["T"] == 1 + extra // 256
+        ref = O.analyze_clip(O.make_config(n, n // 4, sr), x[0])
+        assert util.mag_err(r["mags"][0], ref["mags"]).max() <= 2e-6
+    # digital silence and DC
+    r = an.analyze_host(np.zeros((2, 8192), np.float32))
+    assert (r["mags"] == 0).all() and (r["features"]["n_pitches"] == 0).all()
+    assert (r["features"]["flux"] == 0).all() and (r["features"]["burst_count"] == 0).all()
+    r = an.analyze_host(np.full((1, 8192), 0.25, np.float32))
+    assert (r["features"]["n_pitches"] == 0).all()
+    # full-scale square wave (maximum magnitudes), clipping-level input
+    sq = np.sign(np.sin(2 * np.pi * 1000.0 * np.arange(16384) / sr)).astype(np.float32)[None, :]
+    r = an.analyze_host(sq, want_dbg=True)
+    check_stage_isolated(O, r, 0, n, sr, label="square")
+
+
+def test_noise_floor_db_and_freq_range_parameters(aa, O, torch_cuda):
+    x = signals.multitone(21, 44100.0, 40000)[None, :]
+    for db, fmin, fmax in [(-60.0, 24.0, 10000.0), (-96.0, 200.0, 2000.0), (-30.0, 24.0, 10000.0)]:
+        an = aa.Analyzer(aa.Config(n=2048, sample_rate=44100.0, noise_floor_db=db, min_freq=fmin, max_freq=fmax))
+        res = an.analyze_host(x, want_dbg=True)
+        cfg = O.make_config(2048, 512, 44100.0, fmin, fmax, db)
+        iso = O.analyze_clip(cfg, mags_in=res["mags"][0], want_floor=True, want_peaks=True, want_diag=True)
+        assert np.array_equal(res["dbg_floor"][0], iso["floor"])
+        assert np.array_equal(res["dbg_peaks"][0], iso["peaks"])
+        bad, _ = util.compare_pitch_records(res["features"][0], iso["features"], iso["diag"])
+        assert len(bad) == 0
+
+
+def test_onset_in_drives_the_tracker(aa, O, torch_cuda):
+    x = signals.multitone(33, 44100.0, 60000)[None, :]
+    T = (60000 - 2048) // 512 + 1
+    onset = np.zeros((1, T), np.uint8)
+    onset[0, [20, 21, 50]] = 1
+    res = run_gpu(aa, x, 2048, 44100.0, onset_in=onset)
+    check_stage_isolated(O, res, 0, 2048, 44100.0, onset_in=onset[0], label="onset_in")
+    res0 = run_gpu(aa, x, 2048, 44100.0)
+    assert res["stable"].tobytes() != res0["stable"].tobytes()
+
+
+def test_chunked_stream_with_halo(aa, O, torch_cuda):
+    """cfg4 shape: hop-aligned chunks with a one-window halo, expressed as overlapping clips.
+    Stateless outputs equal the unchunked run bit for bit; stateful ones restart per chunk."""
+    import importlib
+
+    sh = importlib.import_module("audio-analyzer-rs_b200.sharding")
+    n, hop, sr = 2048, 512, 48000.0
+    x = signals.chord_vibrato(0xA0D14, sr, 400000)
+    an = aa.Analyzer(aa.Config(n=n, sample_rate=sr))
+    full = an.analyze_host(x[None, :])
+    nch, clen, stride, tail = sh.uniform_chunks(len(x), n, hop, 96)
+    ch = an.analyze_host(x, clip_len=clen, clip_stride=stride)
+    assert ch["T"] == 96 and ch["mags"].shape[0] == nch
+    Tc = nch * 96
+    assert np.array_equal(ch["mags"].reshape(Tc, -1), full["mags"][0, :Tc])
+    assert np.array_equal(ch["features"]["energy"].reshape(-1), full["features"]["energy"][0, :Tc])
+    assert np.array_equal(ch["features"]["centroid"].reshape(-1), full["features"]["centroid"][0, :Tc])
+    # the first chunk is the start of the stream: everything equal there
+    assert ch["features"][0].tobytes() == full["features"][0, :96].tobytes()
+    # later chunks restart the floors: the pitch set still agrees on most frames
+    agree = (ch["features"]["n_pitches"].reshape(-1) == full["features"]["n_pitches"][0, :Tc]).mean()
+    assert agree > 0.7, agree
+
+
+def test_device_api_many_clips_and_summaries(aa, O, torch_cuda):
+    """Device-resident path: synthetic clips generated on the GPU (SURVEY 8d generator), more clips
+    than SM slots so several waves run; a sample of clips is checked against the oracle and the
+    per-clip summaries against numpy."""
+    torch = torch_cuda
+    n, sr, clip_len, n_clips = 2048, 44100.0, 44100, 700
+    cfg = aa.Config(n=n, sample_rate=sr)
+    an = aa.Analyzer(cfg)
+    T = an.num_frames(clip_len)
+    half = n // 2 + 1
+    clips = torch.empty(n_clips, clip_len, device="cuda", dtype=torch.float32)
+    aa.synth_clips_device(clips.data_ptr(), n_clips, clip_len, clip_len, sr, 0xA0D15)
+    mags = torch.empty(n_clips, T, half, device="cuda", dtype=torch.float32)
+    feat = torch.zeros(n_clips, T, 96, device="cuda", dtype=torch.uint8)
+    stab = torch.zeros(n_clips, T, 136, device="cuda", dtype=torch.uint8)
+    summ = torch.zeros(n_clips, 32, device="cuda", dtype=torch.uint8)
+    s = torch.cuda.current_stream()
+    an.analyze_device(clips.data_ptr(), n_clips, clip_len, clip_len, mags=mags.data_ptr(),
+                      features=feat.data_ptr(), stable=stab.data_ptr(), summaries=summ.data_ptr(),
+                      stream=s.cuda_stream)
+    torch.cuda.synchronize()
+    assert an.last_launches == 2
+    h_clips = clips.cpu().numpy()
+    assert np.isfinite(h_clips).all() and 0.01 < np.abs(h_clips).max() <= 1.0
+    h_feat = feat.cpu().numpy().view(aa.FEATURES_DTYPE).reshape(n_clips, T)
+    h_stab = stab.cpu().numpy().view(aa.STABLE_DTYPE).reshape(n_clips, T)
+    h_summ = summ.cpu().numpy().view(aa.SUMMARY_DTYPE).reshape(n_clips)
+    ocfg = O.make_config(n, n // 4, sr)
+    for c in (0, 1, 147, 148, 333, 699):
+        ref = O.analyze_clip(ocfg, h_clips[c])
+        gm = mags[c].cpu().numpy()
+        assert util.mag_err(gm, ref["mags"]).max() <= 2e-6
+        iso = O.analyze_clip(ocfg, mags_in=gm, want_diag=True)
+        bad, _ = util.compare_pitch_records(h_feat[c], iso["features"], iso["diag"])
+        assert len(bad) == 0
+        assert np.array_equal(h_feat[c]["burst_count"], iso["features"]["burst_count"])
+    # summaries
+    assert (h_summ["n_frames"] == T).all()
+    assert np.array_equal(h_summ["n_pitched"], (h_feat["n_pitches"] > 0).sum(axis=1))
+    assert np.array_equal(h_summ["n_onsets"], ((h_feat["flags"] & 4) != 0).sum(axis=1))
+    assert np.allclose(h_summ["mean_centroid"], h_feat["centroid"].astype(np.float64).mean(axis=1), rtol=1e-6)
+    assert np.allclose(h_summ["mean_energy"], h_feat["energy"].astype(np.float64).mean(axis=1), rtol=1e-6)
+    assert np.array_equal(h_summ["max_energy"], h_feat["energy"].max(axis=1))
+    # determinism: same input twice -> identical bytes
+    feat2 = torch.zeros_like(feat)
+    an.analyze_device(clips.data_ptr(), n_clips, clip_len, clip_len, features=feat2.data_ptr(),
+                      stream=s.cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(feat, feat2)
+    # host path == device path
+    hres = an.analyze_host(h_clips[:300], want_mags=False)
+    assert hres["features"].tobytes() == h_feat[:300].tobytes()
+    assert hres["stable"].tobytes() == h_stab[:300].tobytes()
+    assert hres["summaries"].tobytes() == h_summ[:300].tobytes()
+
+
+def test_full_size_cfg2_properties(aa, O, torch_cuda):
+    """BASELINE configs[1] at full size: 1024 clips x 30 s @ 48 kHz, 4096-pt / hop 1024, all features.
+    Size-independent properties: duplicated clips give identical records (independent of the CTA /
+    SM they ran on), three sampled clips match the oracle, summaries are consistent."""
+    torch = torch_cuda
+    n, sr, clip_len, n_clips = 4096, 48000.0, 1440000, 1024
+    an = aa.Analyzer(aa.Config(n=n, sample_rate=sr))
+    T = an.num_frames(clip_len)
+    assert T == 1403
+    clips = torch.empty(n_clips, clip_len, device="cuda", dtype=torch.float32)
+    aa.synth_clips_device(clips.data_ptr(), n_clips // 2, clip_len, clip_len, sr, 0xA0D10)
+    clips[n_clips // 2:] = clips[: n_clips // 2]          # second half duplicates the first
+    feat = torch.zeros(n_clips, T, 96, device="cuda", dtype=torch.uint8)
+    summ = torch.zeros(n_clips, 32, device="cuda", dtype=torch.uint8)
+    an.analyze_device(clips.data_ptr(), n_clips, clip_len, clip_len, features=feat.data_ptr(),
+                      summaries=summ.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(feat[: n_clips // 2], feat[n_clips // 2:])
+    assert torch.equal(summ[: n_clips // 2], summ[n_clips // 2:])
+    h_feat = feat.cpu().numpy().view(aa.FEATURES_DTYPE).reshape(n_clips, T)
+    assert (h_feat["n_pitches"] > 0).mean() > 0.9          # every clip is tonal
+    ocfg = O.make_config(n, n // 4, sr)
+    for c in (0, 311, 1023):
+        x = clips[c].cpu().numpy()
+        ref = O.analyze_clip(ocfg, x, want_diag=True)
+        agree = (ref["features"]["n_pitches"] == h_feat[c]["n_pitches"]).mean()
+        assert agree > 0.97, agree
+        assert util.ulp_close(ref["features"]["energy"], h_feat[c]["energy"], 1e-5).all()
+        assert (ref["features"]["burst_count"] != h_feat[c]["burst_count"]).mean() < 0.02
