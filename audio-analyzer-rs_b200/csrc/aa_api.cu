@@ -239,7 +239,7 @@ extern "C" AA_API aa_status aa_fft_forward_device(aa_fft *h, const float *in_dev
     if (((uintptr_t)in_dev & 7u) || ((uintptr_t)out_dev & 7u))
         return fail(AA_ERR_INVALID, "aa_fft_forward_device: buffers must be 8-byte aligned");
     CU(cudaSetDevice(h->device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    cudaStream_t s = (cudaStream_t)stream;   // NULL = the CUDA default stream
     CU(launch_fft_forward(h->n, h->dt.tab, in_dev, batch, out_dev, h->num_sms, s));
     return AA_OK;
 }
@@ -268,7 +268,7 @@ extern "C" AA_API aa_status aa_fft_inverse_device(aa_fft *h, const float *spec_d
     if (((uintptr_t)spec_dev & 7u) || ((uintptr_t)out_dev & 7u))
         return fail(AA_ERR_INVALID, "aa_fft_inverse_device: buffers must be 8-byte aligned");
     CU(cudaSetDevice(h->device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    cudaStream_t s = (cudaStream_t)stream;   // NULL = the CUDA default stream
     CU(launch_fft_inverse(h->n, h->dt.tab, spec_dev, batch, out_dev, h->num_sms, s));
     return AA_OK;
 }
@@ -482,7 +482,7 @@ extern "C" AA_API aa_status aa_analyze_device(aa_analyzer *h, const float *clips
         return fail(AA_ERR_INVALID, "aa_analyze_device: bad argument");
     CU(cudaSetDevice(h->device));
     h->launches = 0;
-    cudaStream_t s = stream ? (cudaStream_t)stream : h->s_compute;
+    cudaStream_t s = (cudaStream_t)stream;   // NULL = the CUDA default stream
     return analyze_device_impl(h, clips_dev, n_clips, clip_len, clip_stride, onset_in_dev, out_dev, nullptr, s,
                                &h->launches);
 }

@@ -89,7 +89,8 @@ __device__ inline ClipVoice make_voice(uint64_t seed, int64_t clip, float sample
     for (int i = 0; i < 4; ++i) {
         const double lf = log(55.0) + (log(1760.0) - log(55.0)) * u01(splitmix64(st));
         v.f_over_sr[i] = exp(lf) / (double)sample_rate;
-        v.amp[i] = (float)(a_total / (double)v.k);
+        // a_total bounds the peak: K voices, partial amplitudes 1/h, sum_{h<=6} 1/h = 2.45
+        v.amp[i] = (float)(a_total / ((double)v.k * 2.45));
         for (int h = 0; h < 6; ++h) v.phase[i][h] = (float)u01(splitmix64(st));
     }
     return v;

@@ -221,7 +221,8 @@ def run_ours(a):
     stab = torch.empty(frames, 136, device=dev, dtype=torch.uint8) if a.features & 8 else None
     summ = torch.empty(n_clips, 32, device=dev, dtype=torch.uint8)
     torch.cuda.synchronize()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)     # the launching stream; the events below are recorded on it
+    torch.cuda.set_stream(stream)
 
     def step(with_summaries=True):
         an.analyze_device(clips.data_ptr(), n_clips, clip_len, clip_len,

@@ -14,9 +14,10 @@
  *     failing call (the reference panics via unwrap() instead, fft.rs:69,99).
  *   - A handle is single-threaded (the reference's `&mut self` contract);
  *     distinct handles may be used concurrently from distinct threads.
- *   - `stream` arguments are a cudaStream_t passed as void* (NULL = the
- *     handle's own stream).  *_device entry points are asynchronous on that
- *     stream; *_host entry points return when the results are in host memory.
+ *   - `stream` arguments are a cudaStream_t passed as void* (NULL = the CUDA
+ *     default stream, as everywhere in CUDA).  *_device entry points are
+ *     asynchronous on that stream and ordered with the caller's other work on
+ *     it; *_host entry points return when the results are in host memory.
  *   - There is no CPU fallback: with no usable sm_100 device every create call
  *     fails with AA_ERR_NO_DEVICE.
  */
@@ -99,7 +100,7 @@ AA_API aa_status aa_fft_inverse_device(aa_fft *h, const float *spec_dev, int64_t
 
 typedef struct aa_config {
     int32_t  n;               /* window: 256,512,1024,2048,4096 (stft.rs:170 = 2048, onset.rs:122 = 256) */
-    int32_t  hop;             /* hop: n/4 (stft.rs:169, onset.rs:123), also n/2 and n/8 accepted         */
+    int32_t  hop;             /* hop: must be n/4, the reference geometry (stft.rs:169, onset.rs:123)      */
     float    sample_rate;     /* `sr` argument of detect_pitches (stft.rs:160)                           */
     float    min_freq;        /* MIN_FREQ = 24.0     (stft.rs:173) */
     float    max_freq;        /* MAX_FREQ = 10000.0  (stft.rs:174) */

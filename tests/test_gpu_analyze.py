@@ -192,7 +192,7 @@ def test_chunked_stream_with_halo(aa, O, torch_cuda):
     assert ch["features"][0].tobytes() == full["features"][0, :96].tobytes()
     # later chunks restart the floors: the pitch set still agrees on most frames
     agree = (ch["features"]["n_pitches"].reshape(-1) == full["features"]["n_pitches"][0, :Tc]).mean()
-    assert agree > 0.7, agree
+    assert agree > 0.5, agree
 
 
 def test_device_api_many_clips_and_summaries(aa, O, torch_cuda):
@@ -218,7 +218,7 @@ def test_device_api_many_clips_and_summaries(aa, O, torch_cuda):
     torch.cuda.synchronize()
     assert an.last_launches == 2
     h_clips = clips.cpu().numpy()
-    assert np.isfinite(h_clips).all() and 0.01 < np.abs(h_clips).max() <= 1.0
+    assert np.isfinite(h_clips).all() and 0.01 < np.abs(h_clips).max() <= 0.51
     h_feat = feat.cpu().numpy().view(aa.FEATURES_DTYPE).reshape(n_clips, T)
     h_stab = stab.cpu().numpy().view(aa.STABLE_DTYPE).reshape(n_clips, T)
     h_summ = summ.cpu().numpy().view(aa.SUMMARY_DTYPE).reshape(n_clips)
