@@ -40,6 +40,11 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
     nvcc = _nvcc()
+    extra = []
+    for macro in ("AA_MINB_SCALE",):          # tuning knobs for experiments: env var -> -D
+        if os.environ.get(macro):
+            extra.append(f"-D{macro}={os.environ[macro]}")
+            force = True
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
@@ -50,7 +55,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd), flush=True)
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
