@@ -380,6 +380,8 @@ struct aa_analyzer {
     DeviceTables dt;
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     StageSlot slot[2];
+    unsigned char *scratch = nullptr;   // per-CTA overflow scratch of the analysis kernel
+    int max_grid = 0;
     int64_t launches = 0;
 };
 
@@ -404,6 +406,11 @@ extern "C" AA_API aa_status aa_analyzer_create(const aa_config *cfg, aa_analyzer
         (e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) {
         aa_analyzer_destroy(h);
         return fail_cuda(e, "cudaStreamCreate");
+    }
+    h->max_grid = sms * analyze_ctas_per_sm(cfg->n);
+    if ((e = cudaMalloc(&h->scratch, (size_t)h->max_grid * analyze_scratch_bytes(cfg->n))) != cudaSuccess) {
+        aa_analyzer_destroy(h);
+        return fail_cuda(e, "cudaMalloc(scratch)");
     }
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&h->slot[i].h2d_done, cudaEventDisableTiming);
@@ -433,6 +440,7 @@ extern "C" AA_API aa_status aa_analyzer_destroy(aa_analyzer *h)
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    cudaFree(h->scratch);
     cudaFree(h->dt.mem);
     delete h;
     return AA_OK;
@@ -464,6 +472,8 @@ static aa_status analyze_device_impl(aa_analyzer *h, const float *clips_dev, int
     p.dbg_floor = out->dbg_floor;
     p.dbg_peaks = out->dbg_peaks;
     p.state = state;
+    p.scratch = h->scratch;
+    p.grid = (int)std::min<int64_t>(n_clips, h->max_grid);
     CU(launch_analyze(p, s));
     ++*launches;
     if (out->summaries) {

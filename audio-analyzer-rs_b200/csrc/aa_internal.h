@@ -34,7 +34,8 @@ struct AnalyzeParams {
     float *dbg_floor;
     uint8_t *dbg_peaks;
     float *state;            // [n_clips][state_floats(half)] or nullptr
-    int64_t frame_base;      // streaming: index of the first frame (only affects nothing but bookkeeping)
+    unsigned char *scratch;  // [grid][analyze_scratch_bytes(n)] overflow space for frames with > 256 candidates
+    int grid;                // persistent CTAs: min(n_clips, num_sms * analyze_ctas_per_sm(n))
     Tables tab;
     int n, hop, half;
     float bin_width, min_freq, max_freq;
@@ -46,6 +47,8 @@ struct AnalyzeParams {
 cudaError_t launch_analyze(const AnalyzeParams &p, cudaStream_t s);
 size_t      analyze_smem_bytes(int n);
 int         analyze_threads(int n);
+int         analyze_ctas_per_sm(int n);
+size_t      analyze_scratch_bytes(int n);
 
 cudaError_t launch_fft_forward(int n, const Tables &tab, const float *in, int64_t batch, float *out,
                                int num_sms, cudaStream_t s);
