@@ -153,12 +153,17 @@ __device__ __forceinline__ void fft_reload(float2 (&v)[E], int t, const float2 *
 }
 
 // Per-window-size geometry: E complex elements per thread, NT = N/2/E threads.
+// E trades registers / unrolled code size (instruction-cache footprint) against the number of
+// shared-memory exchanges: 2048 = 16*16*8 (3 passes) or 8*8*8*4 (4 passes).
+#ifndef AA_E_BIG
+#define AA_E_BIG 8
+#endif
 template <int N>
 struct Geo;
 template <>
-struct Geo<4096> { static constexpr int E = 16; };
+struct Geo<4096> { static constexpr int E = AA_E_BIG; };
 template <>
-struct Geo<2048> { static constexpr int E = 16; };
+struct Geo<2048> { static constexpr int E = AA_E_BIG; };
 template <>
 struct Geo<1024> { static constexpr int E = 8; };
 template <>
@@ -166,60 +171,42 @@ struct Geo<512> { static constexpr int E = 8; };
 template <>
 struct Geo<256> { static constexpr int E = 4; };
 
-// Full N/2-point complex FFT of v (in: v[m] = z[t + m*NT]; out: v[m] = Z[t + m*NT]).
-// exA / exB: two padded exchange buffers of padded_len(N/2) float2 each.  Contains
-// the __syncthreads() calls between passes (all threads of the CTA must call it).
+// number of Stockham passes for an N2-point transform with at most E points per thread
+__host__ __device__ constexpr int fft_num_passes(int n2, int e)
+{
+    int p = 0;
+    for (int ns = 1; ns < n2; ns *= (n2 / ns < e ? n2 / ns : e)) ++p;
+    return p;
+}
+
+// Generic pass sequence: radix min(E, remaining) per pass, exchange buffers alternate
+// (pass p writes bufs[p & 1]); `sync` is the barrier among the participating threads and
+// `after_first` runs once right after the first barrier (used to refill the hop ring).
+// On return v[m] = Z[t + m*NT]; the exchange buffer NOT read last is bufs[(passes - 1) & 1].
+template <int N2, int E, int NS, int PASS, class Sync, class Hook>
+__device__ __forceinline__ void fft_run(float2 (&v)[E], int t, float2 *buf0, float2 *buf1,
+                                        const float2 *__restrict__ tw, Sync sync, Hook after_first)
+{
+    constexpr int REM = N2 / NS;
+    constexpr int R = REM < E ? REM : E;
+    constexpr bool LAST = (NS * R == N2);
+    float2 *ex = (PASS & 1) ? buf1 : buf0;
+    fft_pass<N2, E, R, NS, LAST>(v, t, ex, tw);
+    if constexpr (!LAST) {
+        sync();
+        if constexpr (PASS == 0) after_first();
+        fft_reload<N2, E>(v, t, ex);
+        fft_run<N2, E, NS * R, PASS + 1>(v, t, buf0, buf1, tw, sync, after_first);
+    }
+}
+
+// Full N/2-point complex FFT of v (in: v[m] = z[t + m*NT]; out: v[m] = Z[t + m*NT]) for a whole CTA.
+// exA / exB: two padded exchange buffers of padded_len(N/2) float2 each.  Contains __syncthreads().
 template <int N>
 __device__ __forceinline__ void fft_half_complex(float2 (&v)[Geo<N>::E], int t, float2 *exA,
                                                  float2 *exB, const float2 *__restrict__ tw)
 {
-    constexpr int N2 = N / 2;
-    constexpr int E = Geo<N>::E;
-    if constexpr (N == 4096) {              // 2048 = 16 * 16 * 8
-        fft_pass<N2, E, 16, 1, false>(v, t, exA, tw);
-        __syncthreads();
-        fft_reload<N2, E>(v, t, exA);
-        fft_pass<N2, E, 16, 16, false>(v, t, exB, tw);
-        __syncthreads();
-        fft_reload<N2, E>(v, t, exB);
-        fft_pass<N2, E, 8, 256, true>(v, t, nullptr, tw);
-    } else if constexpr (N == 2048) {       // 1024 = 16 * 16 * 4
-        fft_pass<N2, E, 16, 1, false>(v, t, exA, tw);
-        __syncthreads();
-        fft_reload<N2, E>(v, t, exA);
-        fft_pass<N2, E, 16, 16, false>(v, t, exB, tw);
-        __syncthreads();
-        fft_reload<N2, E>(v, t, exB);
-        fft_pass<N2, E, 4, 256, true>(v, t, nullptr, tw);
-    } else if constexpr (N == 1024) {       // 512 = 8 * 8 * 8
-        fft_pass<N2, E, 8, 1, false>(v, t, exA, tw);
-        __syncthreads();
-        fft_reload<N2, E>(v, t, exA);
-        fft_pass<N2, E, 8, 8, false>(v, t, exB, tw);
-        __syncthreads();
-        fft_reload<N2, E>(v, t, exB);
-        fft_pass<N2, E, 8, 64, true>(v, t, nullptr, tw);
-    } else if constexpr (N == 512) {        // 256 = 8 * 8 * 4
-        fft_pass<N2, E, 8, 1, false>(v, t, exA, tw);
-        __syncthreads();
-        fft_reload<N2, E>(v, t, exA);
-        fft_pass<N2, E, 8, 8, false>(v, t, exB, tw);
-        __syncthreads();
-        fft_reload<N2, E>(v, t, exB);
-        fft_pass<N2, E, 4, 64, true>(v, t, nullptr, tw);
-    } else {                                // N == 256: 128 = 4 * 4 * 4 * 2
-        static_assert(N == 256, "unsupported window size");
-        fft_pass<N2, E, 4, 1, false>(v, t, exA, tw);
-        __syncthreads();
-        fft_reload<N2, E>(v, t, exA);
-        fft_pass<N2, E, 4, 4, false>(v, t, exB, tw);
-        __syncthreads();
-        fft_reload<N2, E>(v, t, exB);
-        fft_pass<N2, E, 4, 16, false>(v, t, exA, tw);
-        __syncthreads();
-        fft_reload<N2, E>(v, t, exA);
-        fft_pass<N2, E, 2, 64, true>(v, t, nullptr, tw);
-    }
+    fft_run<N / 2, Geo<N>::E, 1, 0>(v, t, exA, exB, tw, [] { __syncthreads(); }, [] {});
 }
 
 // realfft's split post-pass for one pair: a = Z[k], b = Z[N/2 - k], tw = 0.5*exp(-2 pi i k/N).

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(N / 2 / Geo<N>::E) fft_forward_kernel(const fl
         for (int m = 0; m < E; ++m) v[m] = __ldg(&src[t + m * NT]);
         fft_half_complex<N>(v, t, exA, exB, tab.tw);
 
-        float2 *pbuf = (N == 256) ? exB : exA;
+        float2 *pbuf = ((fft_num_passes(N2, E) - 1) & 1) ? exB : exA;
 #pragma unroll
         for (int m = EH; m < E; ++m) pbuf[padidx(t + m * NT - CBIN)] = v[m];
         if (t == 0) pbuf[padidx(CBIN)] = v[0];
