@@ -474,6 +474,8 @@ static aa_status analyze_device_impl(aa_analyzer *h, const float *clips_dev, int
     p.state = state;
     p.scratch = h->scratch;
     p.grid = (int)std::min<int64_t>(n_clips, h->max_grid);
+    if (state && n_clips > h->max_grid)
+        return fail(AA_ERR_INVALID, "state carry-over needs one clip per resident CTA");
     CU(launch_analyze(p, s));
     ++*launches;
     if (out->summaries) {

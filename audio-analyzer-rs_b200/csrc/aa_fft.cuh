@@ -110,9 +110,16 @@ struct Bfly<16> {
     }
 };
 
+// padidx(j0 + r*NS) == padidx(j0) + r*NS + ((r*NS) >> 4) for every exchange of the plans used here
+// (j0 & 15 never carries into bit 4 when r*NS is added: see tools/stockham_model.py --check-pad), so
+// one padded base address per butterfly is enough and the per-element offsets are immediates.
+__host__ __device__ constexpr int padoff(int d) { return d + (d >> 4); }
+
 // One Stockham pass.  NS = product of the radices already applied.  tw[i] =
-// exp(-2 pi i * i / N2).  If !LAST the butterfly outputs are scattered into `exch`
-// (padded indexing); the caller synchronises and reloads with fft_reload().
+// exp(-2 pi i * i / N2).  The butterfly's R-1 twiddles w^r (w = tw[k*TSTEP]) are built from ONE
+// table load by a product tree of depth <= 4 (<= 4 extra roundings, far inside the magnitude
+// tolerance) instead of R-1 dependent L2-latency loads.  If !LAST the outputs are scattered into
+// `exch` (padded indexing); the caller synchronises and reloads with fft_reload().
 template <int N2, int E, int R, int NS, bool LAST>
 __device__ __forceinline__ void fft_pass(float2 (&v)[E], int t, float2 *exch,
                                          const float2 *__restrict__ tw)
@@ -129,8 +136,16 @@ __device__ __forceinline__ void fft_pass(float2 (&v)[E], int t, float2 *exch,
         const int k = j & (NS - 1);
         if (NS > 1) {
             constexpr int TSTEP = N2 / (NS * R);
+            float2 w[R];
+            w[1] = __ldg(&tw[k * TSTEP]);
 #pragma unroll
-            for (int r = 1; r < R; ++r) x[r] = cmul(x[r], __ldg(&tw[r * k * TSTEP]));
+            for (int r = 2; r < R; ++r) {
+                const int hi = (r >= 8) ? 8 : (r >= 4 ? 4 : 2);   // largest power of two <= r
+                const int lo = r - hi;
+                w[r] = lo ? cmul(w[hi], w[lo]) : cmul(w[hi / 2], w[hi / 2]);
+            }
+#pragma unroll
+            for (int r = 1; r < R; ++r) x[r] = cmul(x[r], w[r]);
         }
         Bfly<R>::run(x);
         if (LAST) {
@@ -138,8 +153,9 @@ __device__ __forceinline__ void fft_pass(float2 (&v)[E], int t, float2 *exch,
             for (int r = 0; r < R; ++r) v[b + r * BPT] = x[r];
         } else {
             const int j0 = (j / NS) * (NS * R) + k;
+            float2 *dst = exch + padidx(j0);
 #pragma unroll
-            for (int r = 0; r < R; ++r) exch[padidx(j0 + r * NS)] = x[r];
+            for (int r = 0; r < R; ++r) dst[padoff(r * NS)] = x[r];
         }
     }
 }
@@ -148,8 +164,10 @@ template <int N2, int E>
 __device__ __forceinline__ void fft_reload(float2 (&v)[E], int t, const float2 *exch)
 {
     constexpr int NT = N2 / E;
+    static_assert(NT % 16 == 0, "reload offsets assume a thread count that is a multiple of 16");
+    const float2 *src = exch + padidx(t);
 #pragma unroll
-    for (int m = 0; m < E; ++m) v[m] = exch[padidx(t + m * NT)];
+    for (int m = 0; m < E; ++m) v[m] = src[padoff(m * NT)];
 }
 
 // Per-window-size geometry: E complex elements per thread, NT = N/2/E threads.
