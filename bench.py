@@ -229,7 +229,7 @@ def run_ours(a):
                           mags=mags.data_ptr() if mags_on else 0, features=feat.data_ptr(),
                           stable=stab.data_ptr() if stab is not None else 0,
                           summaries=summ.data_ptr() if with_summaries else 0, stream=stream.cuda_stream)
-        if world > 1 and with_summaries:
+        if world > 1 and with_summaries and not os.environ.get("AA_BENCH_NO_GATHER"):
             return sh.gather_summaries(summ)     # the only collective: 32 B per clip over NCCL
         return summ
 
