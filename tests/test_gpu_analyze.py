@@ -147,6 +147,29 @@ def test_edge_lengths_and_silence(aa, O, torch_cuda):
     check_stage_isolated(O, r, 0, n, sr, label="square")
 
 
+def test_candidate_overflow_and_general_selection_paths(aa, O, torch_cuda):
+    """More than 256 scoring candidates per frame (the shared-memory candidate list spills to the HBM
+    scratch) and more than 32 survivors of the cutoff (general selection path instead of the
+    lane-resident one): a comb of 300 equal tones with every bin inside the pitch range."""
+    n, sr = 4096, 16000.0
+    rng = np.random.default_rng(42)
+    t = np.arange(n + 12 * (n // 4), dtype=np.float64)
+    x = np.zeros_like(t)
+    for j in range(300):
+        b = 20 + 6 * j + rng.uniform(-0.3, 0.3)
+        x += 0.003 * np.sin(2 * np.pi * b * t / n + rng.uniform(0, 2 * np.pi))
+    x = x.astype(np.float32)[None, :]
+    res = run_gpu(aa, x, n, sr)
+    iso = check_stage_isolated(O, res, 0, n, sr, label="overflow")
+    assert iso["diag"]["n_scored"].max() > 256, iso["diag"]["n_scored"].max()
+    assert (res["features"][0]["n_pitches"] == 8).all()
+    # white noise loud enough that most local maxima are candidates
+    y = (0.2 * rng.standard_normal(x.shape[1])).astype(np.float32)[None, :]
+    res = run_gpu(aa, y, n, sr)
+    iso = check_stage_isolated(O, res, 0, n, sr, label="noise")
+    assert iso["diag"]["n_scored"].max() > 256 and iso["diag"]["n_candidates"].max() > 32
+
+
 def test_noise_floor_db_and_freq_range_parameters(aa, O, torch_cuda):
     x = signals.multitone(21, 44100.0, 40000)[None, :]
     for db, fmin, fmax in [(-60.0, 24.0, 10000.0), (-96.0, 200.0, 2000.0), (-30.0, 24.0, 10000.0)]:
