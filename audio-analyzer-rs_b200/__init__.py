@@ -22,6 +22,9 @@ from ._ffi import (  # noqa: F401
     FLAG_BURST_ONSET,
     FLAG_ENERGY_RISING,
     FLAG_FLUX_ONSET,
+    FLAG_ONSET_FIRED,
+    NOTE_NAMES,
+    NOTE_RECORD_DTYPE,
     FLAG_ONSET_DETECTED,
     FftProcessor,
     STABLE_DTYPE,
@@ -33,6 +36,8 @@ from ._ffi import (  # noqa: F401
     header_symbols,
     lib,
     lib_path,
+    notes_from_stable,
+    notes_from_stable_device,
     num_frames,
     pinned_empty,
     set_device,

@@ -21,7 +21,7 @@ _SO = os.path.join(_HERE, "libaa_gpu.so")
 _HEADER = os.path.join(os.path.dirname(_HERE), "include", "aa_gpu.h")
 
 FEAT_PITCH, FEAT_ONSET, FEAT_CENTROID, FEAT_TRACKER, FEAT_ALL = 1, 2, 4, 8, 15
-FLAG_FLUX_ONSET, FLAG_BURST_ONSET, FLAG_ONSET_DETECTED, FLAG_ENERGY_RISING = 1, 2, 4, 8
+FLAG_FLUX_ONSET, FLAG_BURST_ONSET, FLAG_ONSET_DETECTED, FLAG_ENERGY_RISING, FLAG_ONSET_FIRED = 1, 2, 4, 8, 16
 MAX_NOTES, MAX_STABLE = 8, 16
 
 _PITCH = [("freq", "<f4"), ("score", "<f4")]
@@ -51,6 +51,12 @@ SUMMARY_DTYPE = np.dtype(
         ("max_energy", "<f4"),
     ]
 )
+NOTE_RECORD_DTYPE = np.dtype(
+    [("n", "<u4"), ("reserved", "<u4"),
+     ("note", [("semis", "u1"), ("octave", "u1"), ("reserved", "<u2"), ("cents", "<f4")], (MAX_STABLE,))]
+)
+assert NOTE_RECORD_DTYPE.itemsize == 136
+NOTE_NAMES = ["C", "C#", "D", "D#", "E", "F", "F#", "G", "G#", "A", "A#", "B"]
 STREAM_FRAME_DTYPE = np.dtype(
     [("frame_index", "<i8"), ("features", FEATURES_DTYPE), ("stable", STABLE_DTYPE)]
 )
@@ -149,6 +155,8 @@ def lib():
         "aa_stream_poll": (i32, [vp, vp, i32, C.POINTER(i32)]),
         "aa_stream_reset": (i32, [vp]),
         "aa_synth_clips_device": (i32, [vp, i64, i64, i64, f32, u64, vp]),
+        "aa_notes_from_stable_device": (i32, [vp, i64, f32, vp, vp]),
+        "aa_notes_from_stable_host": (i32, [vp, i64, f32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -381,3 +389,16 @@ def synth_clips_device(ptr: int, n_clips: int, clip_len: int, clip_stride: int, 
                        seed: int, stream: int = 0):
     _check(lib().aa_synth_clips_device(C.c_void_p(ptr), n_clips, clip_len, clip_stride, sample_rate, seed,
                                        C.c_void_p(stream) if stream else None))
+
+
+def notes_from_stable(stable: np.ndarray, base_freq: float = 440.0) -> np.ndarray:
+    """Note::from_freq (theory.rs:195-209) for every stable pitch: records parallel to `stable`."""
+    st = np.ascontiguousarray(stable, STABLE_DTYPE)
+    out = np.zeros(st.shape, NOTE_RECORD_DTYPE)
+    _check(lib().aa_notes_from_stable_host(_ptr(st), st.size, base_freq, _ptr(out)))
+    return out
+
+
+def notes_from_stable_device(stable_ptr: int, n_frames: int, base_freq: float, out_ptr: int, stream: int = 0):
+    _check(lib().aa_notes_from_stable_device(C.c_void_p(stable_ptr), n_frames, base_freq, C.c_void_p(out_ptr),
+                                             C.c_void_p(stream) if stream else None))

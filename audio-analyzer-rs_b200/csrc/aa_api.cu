@@ -807,6 +807,42 @@ extern "C" AA_API aa_status aa_stream_poll(aa_stream *h, aa_stream_frame *out, i
 }
 
 // ---------------------------------------------------------------------------
+// note identification (theory.rs:195-209)
+// ---------------------------------------------------------------------------
+extern "C" AA_API aa_status aa_notes_from_stable_device(const aa_stable_pitches *stable_dev, int64_t n_frames,
+                                                        float base_freq, aa_note_record *notes_dev, void *stream)
+{
+    if (!stable_dev || !notes_dev || n_frames < 0 || !(base_freq > 0.0f))
+        return fail(AA_ERR_INVALID, "aa_notes_from_stable_device: bad argument");
+    aa_status st = check_device(nullptr);
+    if (st != AA_OK) return st;
+    const float base_c0 = base_freq * powf(2.0f, -4.75f);   // theory.rs:197
+    CU(launch_notes(stable_dev, n_frames, base_c0, notes_dev, (cudaStream_t)stream));
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_notes_from_stable_host(const aa_stable_pitches *stable_host, int64_t n_frames,
+                                                      float base_freq, aa_note_record *notes_host)
+{
+    if (!stable_host || !notes_host || n_frames < 0 || !(base_freq > 0.0f))
+        return fail(AA_ERR_INVALID, "aa_notes_from_stable_host: bad argument");
+    if (n_frames == 0) return AA_OK;
+    aa_status st = check_device(nullptr);
+    if (st != AA_OK) return st;
+    aa_stable_pitches *d_in = nullptr;
+    aa_note_record *d_out = nullptr;
+    CU(cudaMalloc(&d_in, sizeof(aa_stable_pitches) * (size_t)n_frames));
+    cudaError_t e = cudaMalloc(&d_out, sizeof(aa_note_record) * (size_t)n_frames);
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, stable_host, sizeof(aa_stable_pitches) * (size_t)n_frames, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_notes(d_in, n_frames, base_freq * powf(2.0f, -4.75f), d_out, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(notes_host, d_out, sizeof(aa_note_record) * (size_t)n_frames, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail_cuda(e, "aa_notes_from_stable_host");
+    return AA_OK;
+}
+
+// ---------------------------------------------------------------------------
 // synthetic clips
 // ---------------------------------------------------------------------------
 extern "C" AA_API aa_status aa_synth_clips_device(float *clips_dev, int64_t n_clips, int64_t clip_len,

@@ -20,7 +20,7 @@ struct Tables {
 // serial chunk hand-off; batch mode passes nullptr and starts fresh).
 //   float bins[4][half]  : nfP (stft.rs:209), vol (:211), prev (:210 == onset.rs:149), nfO (onset.rs:175)
 //   float scalars[8]     : [0] FluxTracker.threshold, [1] energy_ema, [2] frames seen (as float),
-//                          [3] tracker track count
+//                          [3] tracker track count, [4] frames_since_onset, [5] tail state valid
 //   float tracks[3][32]  : freq, score, life (as float)
 __host__ __device__ inline size_t state_floats(int half) { return (size_t)4 * half + 8 + 96; }
 
@@ -57,6 +57,8 @@ cudaError_t launch_fft_inverse(int n, const Tables &tab, const float *spec, int6
 
 cudaError_t launch_summaries(const aa_frame_features *feat, int64_t n_clips, int64_t T,
                              aa_clip_summary *out, cudaStream_t s);
+cudaError_t launch_notes(const aa_stable_pitches *stable, int64_t n_frames, float base_c0,
+                         aa_note_record *out, cudaStream_t s);
 cudaError_t launch_synth(float *clips, int64_t n_clips, int64_t clip_len, int64_t clip_stride,
                          float sample_rate, uint64_t seed, cudaStream_t s);
 

@@ -62,6 +62,45 @@ cudaError_t launch_summaries(const aa_frame_features *feat, int64_t n_clips, int
 }
 
 // ---------------------------------------------------------------------------
+// Note::from_freq (reference src/analysis/theory.rs:195-209) for every stable pitch.
+// One thread per (frame, slot); base_c0 = base_freq * 2^-4.75 is computed on the host.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) notes_kernel(const aa_stable_pitches *__restrict__ stable, int64_t n_frames,
+                                                    float base_c0, aa_note_record *__restrict__ out)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t f = idx / AA_MAX_STABLE;
+    const int slot = (int)(idx % AA_MAX_STABLE);
+    if (f >= n_frames) return;
+    const uint32_t n = stable[f].n;
+    if (slot == 0) { out[f].n = n; out[f].reserved = 0u; }
+    aa_note r;
+    r.semis = 0; r.octave = 0; r.reserved = 0; r.cents = 0.0f;
+    if ((uint32_t)slot < n) {
+        const float freq = stable[f].pitch[slot].freq;
+        const float lg = __fmul_rn(log2f(__fdiv_rn(freq, base_c0)), 1200.0f);          // :198
+        const float o = __fdiv_rn(__fadd_rn(lg, 50.0f), 1200.0f);                      // :199 `as u8` saturates
+        r.octave = (uint8_t)(!(o > 0.0f) ? 0 : (o >= 255.0f ? 255 : (int)o));
+        const float sm = fmodf(roundf(__fdiv_rn(lg, 100.0f)), 12.0f);                  // :200 `as usize` saturates
+        r.semis = (uint8_t)(!(sm > 0.0f) ? 0 : (int)sm);
+        float c = fmodf(lg, 100.0f);                                                   // :201
+        c = c < 50.0f ? c : -__fsub_rn(100.0f, c);                                     // :202-206
+        r.cents = c;
+    }
+    out[f].note[slot] = r;
+}
+
+cudaError_t launch_notes(const aa_stable_pitches *stable, int64_t n_frames, float base_c0, aa_note_record *out,
+                         cudaStream_t s)
+{
+    if (n_frames <= 0) return cudaSuccess;
+    const int64_t total = n_frames * AA_MAX_STABLE;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    notes_kernel<<<grid, 256, 0, s>>>(stable, n_frames, base_c0, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // Synthetic clips.
 // ---------------------------------------------------------------------------
 __host__ __device__ inline uint64_t splitmix64(uint64_t &x)

@@ -94,6 +94,9 @@ AA_API aa_status aa_fft_inverse_device(aa_fft *h, const float *spec_dev, int64_t
 #define AA_FLAG_BURST_ONSET    2u   /* max_excess > 3 && burst_count >= 3  onset.rs:356 */
 #define AA_FLAG_ONSET_DETECTED 4u   /* both                                onset.rs:357 */
 #define AA_FLAG_ENERGY_RISING  8u   /* energy > 1.5 * energy_ema           onset.rs:373 */
+#define AA_FLAG_ONSET_FIRED    16u   /* offline gating of onset.rs:403,535-539: detected && rising &&
+                                       frames_since_onset >= 3 (no metronome ticks, calibration done).
+                                       Velocity (onset.rs:388-389) = clamp(max(flux, 5*max_excess)/50, 0, 1). */
 
 #define AA_MAX_NOTES   8    /* stft.rs:452 MAX_NOTES */
 #define AA_MAX_STABLE 16    /* bound on displayed PitchTracker tracks */
@@ -179,6 +182,23 @@ AA_API aa_status aa_analyze_host(aa_analyzer *h, const float *clips_host, int64_
                                  const uint8_t *onset_in_host, const aa_outputs *out_host);
 /* Number of kernel launches issued by the last aa_analyze_* call on this handle. */
 AA_API int64_t   aa_analyzer_last_launches(const aa_analyzer *h);
+
+/* ------------------------------------------------------------------------- *
+ * Note identification of the tuner stage (NEXT row f2): Note::from_freq
+ * (src/analysis/theory.rs:195-209) applied to every stable pitch, as numbers
+ * (name strings stay on the host: semis 0 = C, 1 = C#, ... 11 = B).
+ * ------------------------------------------------------------------------- */
+typedef struct aa_note { uint8_t semis, octave; uint16_t reserved; float cents; } aa_note;
+typedef struct aa_note_record {           /* 136 bytes, one per frame, parallel to aa_stable_pitches */
+    uint32_t n;
+    uint32_t reserved;
+    aa_note  note[AA_MAX_STABLE];
+} aa_note_record;
+/* base_freq: Tuner.base, 440 Hz by default (tuner.rs, theory.rs:196) */
+AA_API aa_status aa_notes_from_stable_device(const aa_stable_pitches *stable_dev, int64_t n_frames,
+                                             float base_freq, aa_note_record *notes_dev, void *stream);
+AA_API aa_status aa_notes_from_stable_host(const aa_stable_pitches *stable_host, int64_t n_frames,
+                                           float base_freq, aa_note_record *notes_host);
 
 /* ------------------------------------------------------------------------- *
  * Streaming: the thread body of STFT::detect_pitches / OnsetDetector::

@@ -653,6 +653,7 @@ struct aao_onset {
     int floor_initialized;        /* :176 */
     float energy_ema;             /* :160 */
     float threshold;              /* FluxTracker.threshold :49,59 */
+    uint32_t frames_since_onset;  /* :200, starts at 4 */
 };
 
 aao_onset *aao_onset_create(int half)
@@ -661,6 +662,7 @@ aao_onset *aao_onset_create(int half)
     s->half = half;
     s->prev_magnitude = (float *)calloc((size_t)half, sizeof(float));
     s->noise_floor_per_bin = (float *)calloc((size_t)half, sizeof(float));
+    s->frames_since_onset = 4;
     return s;
 }
 
@@ -677,6 +679,7 @@ void aao_onset_reset(aao_onset *s)
     s->floor_initialized = 0;
     s->energy_ema = 0.0f;
     s->threshold = 0.0f;
+    s->frames_since_onset = 4;
 }
 
 void aao_onset_frame(aao_onset *s, const float *current_mags, float global_floor,
@@ -738,6 +741,11 @@ void aao_onset_frame(aao_onset *s, const float *current_mags, float global_floor
     int bin_burst_onset = max_bin_excess > 3.0f && bin_burst_count >= 3;  /* :356 */
     int onset_detected = flux_onset && bin_burst_onset;                   /* :357 */
     int energy_rising = frame_energy > s->energy_ema * 1.5f;              /* :373 */
+    /* offline reading of :383-456 and :535-539: no metronome ticks to guard against
+     * (suppressed_by_tick = false) and calibration already done */
+    int onset_fired = onset_detected && energy_rising && s->frames_since_onset >= 3;   /* :403 */
+    if (onset_fired || (onset_detected && s->frames_since_onset < 3)) s->frames_since_onset = 0;  /* :535 */
+    else if (s->frames_since_onset != 0xffffffffu) s->frames_since_onset += 1;          /* saturating_add */
 
     out->flux = current_flux;
     out->energy = frame_energy;
@@ -746,7 +754,24 @@ void aao_onset_frame(aao_onset *s, const float *current_mags, float global_floor
     out->energy_ema = s->energy_ema;
     out->flags = (flux_onset ? AAO_FLAG_FLUX_ONSET : 0u) | (bin_burst_onset ? AAO_FLAG_BURST_ONSET : 0u)
                | (onset_detected ? AAO_FLAG_ONSET_DETECTED : 0u)
-               | (energy_rising ? AAO_FLAG_ENERGY_RISING : 0u);
+               | (energy_rising ? AAO_FLAG_ENERGY_RISING : 0u)
+               | (onset_fired ? AAO_FLAG_ONSET_FIRED : 0u);
+}
+
+/* f2: Note::from_freq, analysis/theory.rs:195-209 */
+void aao_note_from_freq(float freq, float base_freq, int *octave, int *semis, float *cents)
+{
+    float base = base_freq * powf(2.0f, -4.75f);                  /* :197 */
+    float lg = log2f(freq / base) * 1200.0f;                      /* :198 */
+    float o = (lg + 50.0f) / 1200.0f;                             /* :199 `as u8` saturates */
+    int oct = !(o > 0.0f) ? 0 : (o >= 255.0f ? 255 : (int)o);
+    float sm = fmodf(roundf(lg / 100.0f), 12.0f);                 /* :200 `as usize` saturates */
+    int se = !(sm > 0.0f) ? 0 : (int)sm;
+    float c = fmodf(lg, 100.0f);                                  /* :201 */
+    c = c < 50.0f ? c : -(100.0f - c);                            /* :202-206 */
+    *octave = oct;
+    *semis = se;
+    *cents = c;
 }
 
 /* a13 (NEW, no reference): spectral centroid in Hz */

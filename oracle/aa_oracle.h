@@ -40,6 +40,9 @@ extern "C" {
 #define AAO_FLAG_BURST_ONSET    2u  /* max_excess > 3 && count >= 3         onset.rs:356 */
 #define AAO_FLAG_ONSET_DETECTED 4u  /* both                                 onset.rs:357 */
 #define AAO_FLAG_ENERGY_RISING  8u  /* energy > ema * 1.5 (post-update ema) onset.rs:373 */
+#define AAO_FLAG_ONSET_FIRED    16u  /* offline gating: detected && rising && frames_since_onset >= 3
+                                        (onset.rs:403,535-539; tick guard and calibration need a live
+                                        transport and are treated as passed) */
 
 #define AAO_MAX_NOTES   8   /* stft.rs:452 */
 #define AAO_MAX_STABLE 16   /* bound on displayed PitchTracker tracks, see aa_oracle.c */
@@ -142,6 +145,11 @@ void aao_onset_destroy(aao_onset *s);
 void aao_onset_reset(aao_onset *s);
 /* fills flux, energy, burst_count, max_excess, flags, energy_ema of *out */
 void aao_onset_frame(aao_onset *s, const float *mags, float global_floor, aao_features *out);
+
+/* ---- f2 (next row): Note::from_freq, analysis/theory.rs:195-209.  PINNED by the reference's own
+ * known-answer tests (theory.rs:405-448): 440 -> A4 with |cents| < 2, 261.626 -> C4, C#4, cents in
+ * [-50, 50].  semis: 0 = C .. 11 = B. */
+void aao_note_from_freq(float freq, float base_freq, int *octave, int *semis, float *cents);
 
 /* ---- a13: spectral centroid (NEW, self-defined): sum(k*bw*m)/sum(m), f64 acc --- */
 float aao_centroid(const float *mags, int half, float bin_width);

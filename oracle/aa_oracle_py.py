@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libaa_oracle.so")
 
 FEAT_PITCH, FEAT_ONSET, FEAT_CENTROID, FEAT_TRACKER = 1, 2, 4, 8
-FLAG_FLUX_ONSET, FLAG_BURST_ONSET, FLAG_ONSET_DETECTED, FLAG_ENERGY_RISING = 1, 2, 4, 8
+FLAG_FLUX_ONSET, FLAG_BURST_ONSET, FLAG_ONSET_DETECTED, FLAG_ENERGY_RISING, FLAG_ONSET_FIRED = 1, 2, 4, 8, 16
 MAX_NOTES, MAX_STABLE = 8, 16
 
 FEATURES_DTYPE = np.dtype(
@@ -128,6 +128,7 @@ def lib():
     L.aao_onset_frame.argtypes = [vp, fp, C.c_float, vp]
     L.aao_centroid.restype = C.c_float
     L.aao_centroid.argtypes = [fp, C.c_int, C.c_float]
+    L.aao_note_from_freq.argtypes = [C.c_float, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int), fp]
     L.aao_yin_lag.restype = C.c_int
     L.aao_yin_lag.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_float, dp]
     L.aao_num_frames.restype = C.c_int64
@@ -258,6 +259,16 @@ class Onset:
 def centroid(mags, bin_width):
     mags = np.ascontiguousarray(mags, np.float32)
     return float(lib().aao_centroid(_fp(mags), mags.shape[0], bin_width))
+
+
+NOTE_NAMES = ["C", "C#", "D", "D#", "E", "F", "F#", "G", "G#", "A", "A#", "B"]
+
+
+def note_from_freq(freq, base_freq=440.0):
+    """Note::from_freq (theory.rs:195-209) -> (name like 'A4', octave, semis, cents)."""
+    o, s_, c = C.c_int(0), C.c_int(0), C.c_float(0)
+    lib().aao_note_from_freq(freq, base_freq, C.byref(o), C.byref(s_), C.byref(c))
+    return f"{NOTE_NAMES[s_.value]}{o.value}", o.value, s_.value, c.value
 
 
 def yin_lag(frame, min_lag, max_lag, threshold=0.1):

@@ -218,6 +218,7 @@ class OnsetNp:
         self.init = False
         self.ema = F(0.0)
         self.thr = F(0.0)
+        self.since = 4            # frames_since_onset, onset.rs:200
 
     def frame(self, m, gf):
         half = self.half
@@ -258,8 +259,14 @@ class OnsetNp:
         flux_onset = bool(is_on and flux > F(self.thr * F(1.5)))
         burst_onset = bool(max_ex > F(3.0) and count >= 3)
         rising = bool(energy > F(self.ema * F(1.5)))
+        detected = flux_onset and burst_onset
+        fired = detected and rising and self.since >= 3          # onset.rs:403 (no ticks, calibrated)
+        if fired or (detected and self.since < 3):               # onset.rs:535-539
+            self.since = 0
+        else:
+            self.since += 1
         flags = (1 if flux_onset else 0) | (2 if burst_onset else 0) | \
-                (4 if (flux_onset and burst_onset) else 0) | (8 if rising else 0)
+                (4 if detected else 0) | (8 if rising else 0) | (16 if fired else 0)
         return flux, energy, count, max_ex, flags, self.ema
 
 

@@ -303,3 +303,33 @@ def test_full_size_cfg2_properties(aa, O, torch_cuda):
         assert agree > 0.97, agree
         assert util.ulp_close(ref["features"]["energy"], h_feat[c]["energy"], 1e-5).all()
         assert (ref["features"]["burst_count"] != h_feat[c]["burst_count"]).mean() < 0.02
+
+
+def test_note_records_match_reference_from_freq(aa, O, torch_cuda):
+    """NEXT row f2: Note::from_freq (theory.rs:195-209) on the device for every stable pitch."""
+    x = np.stack([signals.sine(440.0, 44100.0, 30000), signals.multitone(3, 44100.0, 30000)])
+    res = run_gpu(aa, x, 2048, 44100.0, dbg=False)
+    notes = aa.notes_from_stable(res["stable"])
+    assert notes.shape == res["stable"].shape
+    assert np.array_equal(notes["n"], res["stable"]["n"])
+    a4 = notes[0][5]
+    assert a4["n"] == 1 and aa.NOTE_NAMES[a4["note"][0]["semis"]] == "A" and a4["note"][0]["octave"] == 4
+    assert abs(a4["note"][0]["cents"] - 0.77) < 0.05        # 440.196 Hz is +0.77 cents
+    checked = 0
+    for c in range(2):
+        for t in range(res["T"]):
+            for i in range(int(res["stable"][c][t]["n"])):
+                f = float(res["stable"][c][t]["pitch"][i]["freq"])
+                _, octave, semis, cents = O.note_from_freq(f)
+                g = notes[c][t]["note"][i]
+                if abs(abs(cents) - 50.0) < 0.01:
+                    continue                                  # semitone boundary: log2 ulp near-tie
+                assert (int(g["octave"]), int(g["semis"])) == (octave, semis)
+                assert abs(float(g["cents"]) - cents) < 2e-3  # 1 ulp of log2 * 1200 at ~5000 cents
+                checked += 1
+    assert checked > 100
+    # unused slots are zero
+    assert (notes["note"]["cents"][res["stable"]["n"] == 0] == 0).all()
+    # other base frequency
+    n2 = aa.notes_from_stable(res["stable"][0:1, 5:6], base_freq=415.0)
+    assert aa.NOTE_NAMES[n2[0, 0]["note"][0]["semis"]] == "A#"

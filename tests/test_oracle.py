@@ -183,3 +183,36 @@ def test_batch_driver_matches_single(O):
         assert np.array_equal(b["mags"][c], r["mags"])
         assert b["features"][c].tobytes() == r["features"].tobytes()
         assert b["stable"][c].tobytes() == r["stable"].tobytes()
+
+
+def test_note_from_freq_reference_known_answers(O):
+    """The reference's own tests pin this function (analysis/theory.rs:405-448)."""
+    name, octave, semis, cents = O.note_from_freq(440.0)
+    assert name == "A4" and abs(cents) < 2.0                        # theory.rs:405-419
+    assert O.note_from_freq(261.626)[0] == "C4"                     # theory.rs:421-425
+    c_sharp_4 = float(np.float32(261.626) * np.float32(2.0) ** np.float32(1.0 / 12.0))
+    assert O.note_from_freq(c_sharp_4)[0] == "C#4"                  # theory.rs:427-433
+    for f in (261.63, 293.66, 329.63, 349.23, 392.0, 440.0, 493.88, 523.25):   # theory.rs:435-448
+        assert -50.0 <= O.note_from_freq(f)[3] <= 50.0
+    # a quarter tone above A4 flips to A#4 with negative cents; other base frequencies shift the grid
+    assert O.note_from_freq(440.0 * 2 ** (0.6 / 12))[0] == "A#4"
+    assert O.note_from_freq(415.0, base_freq=415.0)[0] == "A4"
+    assert O.note_from_freq(1.0)[1] == 0                            # below C0: `as u8` saturates at 0
+
+
+def test_onset_fired_gating(O):
+    """Offline reading of onset.rs:403,535-539: an onset fires only if detected && energy rising and at
+    least three frames after the previous detection; detections inside the gap restart it."""
+    x = signals.note_sequence(3, 48000.0, 24000)
+    r = O.analyze_clip(O.make_config(256, 64, 48000.0, features=O.FEAT_ONSET), x)
+    fl = r["features"]["flags"]
+    det = (fl & O.FLAG_ONSET_DETECTED) != 0
+    rising = (fl & O.FLAG_ENERGY_RISING) != 0
+    fired = (fl & O.FLAG_ONSET_FIRED) != 0
+    assert 1 <= fired.sum() <= det.sum()
+    assert not (fired & ~(det & rising)).any()
+    since = 4
+    for t in range(len(fl)):
+        want = bool(det[t] and rising[t] and since >= 3)
+        assert bool(fired[t]) == want
+        since = 0 if (want or (det[t] and since < 3)) else since + 1
