@@ -31,6 +31,7 @@ from ._ffi import (  # noqa: F401
     STREAM_FRAME_DTYPE,
     SUMMARY_DTYPE,
     Stream,
+    YinConfig,
     device_count,
     exported_symbols,
     header_symbols,
@@ -42,6 +43,8 @@ from ._ffi import (  # noqa: F401
     pinned_empty,
     set_device,
     synth_clips_device,
+    yin_device,
+    yin_host,
 )
 from .build import build as build_native  # noqa: F401
 

@@ -155,6 +155,8 @@ def lib():
         "aa_stream_poll": (i32, [vp, vp, i32, C.POINTER(i32)]),
         "aa_stream_reset": (i32, [vp]),
         "aa_synth_clips_device": (i32, [vp, i64, i64, i64, f32, u64, vp]),
+        "aa_yin_device": (i32, [vp, vp, i64, i64, i64, vp, vp, vp]),
+        "aa_yin_host": (i32, [vp, vp, i64, i64, i64, vp, vp]),
         "aa_notes_from_stable_device": (i32, [vp, i64, f32, vp, vp]),
         "aa_notes_from_stable_host": (i32, [vp, i64, f32, vp]),
     }
@@ -402,3 +404,27 @@ def notes_from_stable(stable: np.ndarray, base_freq: float = 440.0) -> np.ndarra
 def notes_from_stable_device(stable_ptr: int, n_frames: int, base_freq: float, out_ptr: int, stream: int = 0):
     _check(lib().aa_notes_from_stable_device(C.c_void_p(stable_ptr), n_frames, base_freq, C.c_void_p(out_ptr),
                                              C.c_void_p(stream) if stream else None))
+
+
+class YinConfig(C.Structure):
+    _fields_ = [("n", C.c_int32), ("hop", C.c_int32), ("min_lag", C.c_int32), ("max_lag", C.c_int32),
+                ("threshold", C.c_float)]
+
+
+def yin_host(clips: np.ndarray, n: int, hop: int, min_lag: int, max_lag: int, threshold: float = 0.1):
+    """YIN-style lag search per frame (a14, NEW): returns (lag int32 [n_clips, T], d'(lag) float32)."""
+    clips = np.ascontiguousarray(np.atleast_2d(clips), np.float32)
+    n_clips, clip_len = clips.shape
+    T = 0 if clip_len < n else (clip_len - n) // hop + 1
+    lag = np.zeros((n_clips, T), np.int32)
+    cm = np.zeros((n_clips, T), np.float32)
+    cfg = YinConfig(n, hop, min_lag, max_lag, threshold)
+    _check(lib().aa_yin_host(C.byref(cfg), _ptr(clips), n_clips, clip_len, clip_len, _ptr(lag), _ptr(cm)))
+    return lag, cm
+
+
+def yin_device(cfg: YinConfig, clips_ptr: int, n_clips: int, clip_len: int, clip_stride: int, lag_ptr: int,
+               cmnd_ptr: int = 0, stream: int = 0):
+    _check(lib().aa_yin_device(C.byref(cfg), C.c_void_p(clips_ptr), n_clips, clip_len, clip_stride,
+                               C.c_void_p(lag_ptr), C.c_void_p(cmnd_ptr) if cmnd_ptr else None,
+                               C.c_void_p(stream) if stream else None))

@@ -843,6 +843,64 @@ extern "C" AA_API aa_status aa_notes_from_stable_host(const aa_stable_pitches *s
 }
 
 // ---------------------------------------------------------------------------
+// YIN-style lag search (a14, NEW)
+// ---------------------------------------------------------------------------
+static aa_status yin_check(const aa_yin_config *cfg, int64_t clip_len, int64_t *T)
+{
+    if (!cfg) return fail(AA_ERR_INVALID, "yin config is null");
+    if (cfg->n < 8 || cfg->n > 8192 || cfg->hop <= 0) return fail(AA_ERR_UNSUPPORTED, "yin: 8 <= n <= 8192, hop > 0");
+    if (cfg->min_lag < 1 || cfg->max_lag < cfg->min_lag || cfg->max_lag >= cfg->n)
+        return fail(AA_ERR_INVALID, "yin: need 1 <= min_lag <= max_lag < n");
+    *T = clip_len < cfg->n ? 0 : (clip_len - cfg->n) / cfg->hop + 1;
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_yin_device(const aa_yin_config *cfg, const float *clips_dev, int64_t n_clips,
+                                          int64_t clip_len, int64_t clip_stride, int32_t *lag_dev, float *cmnd_dev,
+                                          void *stream)
+{
+    int64_t T = 0;
+    aa_status st = yin_check(cfg, clip_len, &T);
+    if (st != AA_OK) return st;
+    if (!clips_dev || !lag_dev || n_clips < 0 || clip_stride < 0) return fail(AA_ERR_INVALID, "aa_yin_device: bad argument");
+    int sms = 0;
+    st = check_device(&sms);
+    if (st != AA_OK) return st;
+    CU(launch_yin(clips_dev, n_clips, clip_stride, T, cfg->n, cfg->hop, cfg->min_lag, cfg->max_lag, cfg->threshold,
+                  lag_dev, cmnd_dev, sms, (cudaStream_t)stream));
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_yin_host(const aa_yin_config *cfg, const float *clips_host, int64_t n_clips,
+                                        int64_t clip_len, int64_t clip_stride, int32_t *lag_host, float *cmnd_host)
+{
+    int64_t T = 0;
+    aa_status st = yin_check(cfg, clip_len, &T);
+    if (st != AA_OK) return st;
+    if (!clips_host || !lag_host || n_clips < 0 || clip_stride < 0) return fail(AA_ERR_INVALID, "aa_yin_host: bad argument");
+    if (n_clips == 0 || T == 0) return AA_OK;
+    int sms = 0;
+    st = check_device(&sms);
+    if (st != AA_OK) return st;
+    const size_t span = (size_t)((n_clips - 1) * clip_stride + clip_len);
+    const size_t frames = (size_t)(n_clips * T);
+    float *d_in = nullptr, *d_c = nullptr;
+    int32_t *d_lag = nullptr;
+    cudaError_t e = cudaMalloc(&d_in, span * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_lag, frames * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_c, frames * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, clips_host, span * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = launch_yin(d_in, n_clips, clip_stride, T, cfg->n, cfg->hop, cfg->min_lag, cfg->max_lag, cfg->threshold, d_lag,
+                       d_c, sms, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(lag_host, d_lag, frames * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && cmnd_host) e = cudaMemcpy(cmnd_host, d_c, frames * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_lag); cudaFree(d_c);
+    if (e != cudaSuccess) return fail_cuda(e, "aa_yin_host");
+    return AA_OK;
+}
+
+// ---------------------------------------------------------------------------
 // synthetic clips
 // ---------------------------------------------------------------------------
 extern "C" AA_API aa_status aa_synth_clips_device(float *clips_dev, int64_t n_clips, int64_t clip_len,

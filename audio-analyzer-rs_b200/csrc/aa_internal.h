@@ -57,6 +57,9 @@ cudaError_t launch_fft_inverse(int n, const Tables &tab, const float *spec, int6
 
 cudaError_t launch_summaries(const aa_frame_features *feat, int64_t n_clips, int64_t T,
                              aa_clip_summary *out, cudaStream_t s);
+cudaError_t launch_yin(const float *clips, int64_t n_clips, int64_t clip_stride, int64_t T, int n, int hop,
+                       int min_lag, int max_lag, float threshold, int32_t *lag_out, float *cmnd_out,
+                       int num_sms, cudaStream_t s);
 cudaError_t launch_notes(const aa_stable_pitches *stable, int64_t n_frames, float base_c0,
                          aa_note_record *out, cudaStream_t s);
 cudaError_t launch_synth(float *clips, int64_t n_clips, int64_t clip_len, int64_t clip_stride,

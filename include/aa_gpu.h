@@ -201,6 +201,25 @@ AA_API aa_status aa_notes_from_stable_host(const aa_stable_pitches *stable_host,
                                            float base_freq, aa_note_record *notes_host);
 
 /* ------------------------------------------------------------------------- *
+ * YIN-style lag search per frame (NEW, no reference code; the north_star asks
+ * for "autocorrelation or YIN-style lag search").  On the raw (unwindowed) frame
+ *   d(tau) = sum_{j<W} (x[j]-x[j+tau])^2, W = n - max_lag;  d'(tau) = d(tau)*tau / sum_{j<=tau} d(j)
+ *   lag = first tau >= min_lag with d'(tau) < threshold, advanced to the local minimum; otherwise the
+ *         arg-min of d' over [min_lag, max_lag].           frequency estimate = sample_rate / lag.
+ * Frames as in aa_num_frames (n, hop); lag_out / cmnd_out: [n_clips*T] (cmnd_out may be NULL).
+ * ------------------------------------------------------------------------- */
+typedef struct aa_yin_config {
+    int32_t n, hop;            /* frame length (<= 8192) and hop */
+    int32_t min_lag, max_lag;  /* 1 <= min_lag <= max_lag < n */
+    float   threshold;         /* 0.1 in the YIN paper */
+} aa_yin_config;
+AA_API aa_status aa_yin_device(const aa_yin_config *cfg, const float *clips_dev, int64_t n_clips,
+                               int64_t clip_len, int64_t clip_stride, int32_t *lag_dev, float *cmnd_dev,
+                               void *stream);
+AA_API aa_status aa_yin_host(const aa_yin_config *cfg, const float *clips_host, int64_t n_clips,
+                             int64_t clip_len, int64_t clip_stride, int32_t *lag_host, float *cmnd_host);
+
+/* ------------------------------------------------------------------------- *
  * Streaming: the thread body of STFT::detect_pitches / OnsetDetector::
  * detect_onsets with the SlotPool -> private ring hand-off (stft.rs:240-266,
  * onset.rs:216-237, audio_io/mod.rs:32-79) replaced by a pinned-host +

@@ -333,3 +333,34 @@ def test_note_records_match_reference_from_freq(aa, O, torch_cuda):
     # other base frequency
     n2 = aa.notes_from_stable(res["stable"][0:1, 5:6], base_freq=415.0)
     assert aa.NOTE_NAMES[n2[0, 0]["note"][0]["semis"]] == "A#"
+
+
+def test_yin_lag_search_matches_oracle(aa, O, torch_cuda):
+    """a14 (NEW, self-defined): YIN-style lag search on the GPU vs the float64 oracle: lag indices equal
+    except near-ties (flat d' around the threshold / the minimum), d'(lag) within 1e-4."""
+    sr, n, hop = 48000.0, 2048, 512
+    rng = np.random.default_rng(3)
+    clips = np.stack([signals.sine(f0, sr, 20000, 0.5) + 0.3 * signals.sine(2 * f0, sr, 20000, 0.5, 1.0)
+                      for f0 in (110.0, 220.0, 329.6, 441.0, 987.8)]
+                     + [signals.multitone(8, sr, 20000), (0.1 * rng.standard_normal(20000)).astype(np.float32)])
+    min_lag, max_lag = 24, 1024
+    lag, cm = aa.yin_host(clips, n, hop, min_lag, max_lag, 0.1)
+    T = (20000 - n) // hop + 1
+    assert lag.shape == (len(clips), T)
+    mism = 0
+    for c in range(len(clips)):
+        for t in range(0, T, 3):
+            fr = clips[c, t * hop: t * hop + n]
+            want, dp = O.yin_lag(fr, min_lag, max_lag, 0.1)
+            got = int(lag[c, t])
+            if got != want:
+                # a near-tie: the oracle's d' at the two lags (or at the threshold) is within 1e-4
+                assert abs(dp[got] - dp[want]) < 2e-4 or abs(dp[min(got, want)] - 0.1) < 2e-4, (c, t, got, want)
+                mism += 1
+            else:
+                assert abs(float(cm[c, t]) - dp[want]) < 1e-4 + 1e-3 * dp[want]
+    assert mism <= 3
+    # pure tones: lag == round(sr / f0)
+    assert abs(int(lag[0, 5]) - round(sr / 110.0)) <= 1 and abs(int(lag[3, 5]) - round(sr / 441.0)) <= 1
+    with pytest.raises(aa.AAError):
+        aa.yin_host(clips, n, hop, 0, 1024)
