@@ -381,6 +381,7 @@ struct aa_analyzer {
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     StageSlot slot[2];
     unsigned char *scratch = nullptr;   // per-CTA overflow scratch of the analysis kernel
+    unsigned long long *work_counter = nullptr;   // clip queue of the persistent CTAs
     int max_grid = 0;
     int64_t launches = 0;
 };
@@ -408,7 +409,8 @@ extern "C" AA_API aa_status aa_analyzer_create(const aa_config *cfg, aa_analyzer
         return fail_cuda(e, "cudaStreamCreate");
     }
     h->max_grid = sms * analyze_ctas_per_sm(cfg->n);
-    if ((e = cudaMalloc(&h->scratch, (size_t)h->max_grid * analyze_scratch_bytes(cfg->n))) != cudaSuccess) {
+    if ((e = cudaMalloc(&h->scratch, (size_t)h->max_grid * analyze_scratch_bytes(cfg->n))) != cudaSuccess ||
+        (e = cudaMalloc(&h->work_counter, sizeof(unsigned long long))) != cudaSuccess) {
         aa_analyzer_destroy(h);
         return fail_cuda(e, "cudaMalloc(scratch)");
     }
@@ -441,6 +443,7 @@ extern "C" AA_API aa_status aa_analyzer_destroy(aa_analyzer *h)
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     cudaFree(h->scratch);
+    cudaFree(h->work_counter);
     cudaFree(h->dt.mem);
     delete h;
     return AA_OK;
@@ -476,6 +479,13 @@ static aa_status analyze_device_impl(aa_analyzer *h, const float *clips_dev, int
     p.grid = (int)std::min<int64_t>(n_clips, h->max_grid);
     if (state && n_clips > h->max_grid)
         return fail(AA_ERR_INVALID, "state carry-over needs one clip per resident CTA");
+    // more clips than resident CTAs: hand them out through a device-wide queue so that every SM ends up
+    // with the same amount of work to within one clip
+    p.work_counter = nullptr;
+    if (n_clips > p.grid) {
+        CU(cudaMemsetAsync(h->work_counter, 0, sizeof(unsigned long long), s));
+        p.work_counter = h->work_counter;
+    }
     CU(launch_analyze(p, s));
     ++*launches;
     if (out->summaries) {

@@ -36,6 +36,7 @@ struct AnalyzeParams {
     float *state;            // [n_clips][state_floats(half)] or nullptr
     unsigned char *scratch;  // [grid][analyze_scratch_bytes(n)] overflow space for frames with > 256 candidates
     int grid;                // persistent CTAs: min(n_clips, num_sms * analyze_ctas_per_sm(n))
+    unsigned long long *work_counter;   // device-wide clip queue (zeroed before the launch) or nullptr = static
     Tables tab;
     int n, hop, half;
     float bin_width, min_freq, max_freq;
