@@ -16,13 +16,19 @@
 
 namespace aa {
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex arithmetic on the packed f32x2 pipe (sm_100: FADD2 / FMUL2 / FFMA2 do two IEEE f32 operations per
+// issue slot; operand swaps, per-half negation and scalar broadcast are free operand modifiers).  The kernels
+// built from these are issue-bound, so a complex add is ONE instruction and a complex multiply TWO.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    // a.x * (b.x, b.y) + a.y * (-b.y, b.x)
+    return __ffma2_rn(make_float2(a.x, a.x), b, __fmul2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x)));
 }
 __device__ __forceinline__ float2 cmul_negi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+__device__ __forceinline__ float2 cmul_posi(float2 a) { return make_float2(-a.y, a.x); }  // a * (+i)
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
 
 // exchange-buffer padding: one float2 every 16 keeps both the strided writes of the
 // first pass and the unit-stride reads at the ideal wavefront count.
@@ -67,9 +73,9 @@ struct Bfly<8> {
         Bfly<4>::run(e);
         Bfly<4>::run(o);
         // o[k] *= exp(-2 pi i k / 8)
-        float2 o1 = make_float2(C * (o[1].x + o[1].y), C * (o[1].y - o[1].x));
+        float2 o1 = cscale(cadd(o[1], cmul_negi(o[1])), C);      //  C * (x + y, y - x)
         float2 o2 = cmul_negi(o[2]);
-        float2 o3 = make_float2(C * (o[3].y - o[3].x), -C * (o[3].x + o[3].y));
+        float2 o3 = cscale(cadd(o[3], cmul_posi(o[3])), -C);     // -C * (x - y, x + y)
         x[0] = cadd(e[0], o[0]);
         x[4] = csub(e[0], o[0]);
         x[1] = cadd(e[1], o1);
@@ -96,11 +102,11 @@ struct Bfly<16> {
         float2 w[8];
         w[0] = o[0];
         w[1] = cmul(o[1], make_float2(C1, -S1));
-        w[2] = make_float2(C * (o[2].x + o[2].y), C * (o[2].y - o[2].x));
+        w[2] = cscale(cadd(o[2], cmul_negi(o[2])), C);
         w[3] = cmul(o[3], make_float2(S1, -C1));
         w[4] = cmul_negi(o[4]);
         w[5] = cmul(o[5], make_float2(-S1, -C1));
-        w[6] = make_float2(C * (o[6].y - o[6].x), -C * (o[6].x + o[6].y));
+        w[6] = cscale(cadd(o[6], cmul_posi(o[6])), -C);
         w[7] = cmul(o[7], make_float2(-C1, -S1));
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -232,14 +238,15 @@ __device__ __forceinline__ void fft_half_complex(float2 (&v)[Geo<N>::E], int t, 
 // X[0] = (re+im, 0) and X[N/2] = (re-im, 0).
 __device__ __forceinline__ void rfft_postpass(float2 a, float2 b, float2 tw, float2 &lo, float2 &hi)
 {
-    const float sum_re = a.x + b.x, sum_im = a.y + b.y;
-    const float diff_re = a.x - b.x, diff_im = a.y - b.y;
-    const float half_sum_re = 0.5f * sum_re;
-    const float half_diff_im = 0.5f * diff_im;
-    const float otr = sum_im * tw.x + diff_re * tw.y;
-    const float oti = sum_im * tw.y - diff_re * tw.x;
-    lo = make_float2(half_sum_re + otr, half_diff_im + oti);
-    hi = make_float2(half_sum_re - otr, oti - half_diff_im);
+    const float2 bc = make_float2(b.x, -b.y);
+    const float2 P = cadd(a, bc);                 // (sum_re, diff_im)
+    const float2 Q = csub(a, bc);                 // (diff_re, sum_im)
+    // ot = sum_im * tw + diff_re * (tw.y, -tw.x)
+    const float2 ot = __ffma2_rn(make_float2(Q.y, Q.y), tw, __fmul2_rn(make_float2(Q.x, Q.x), make_float2(tw.y, -tw.x)));
+    const float2 h = make_float2(0.5f, 0.5f);
+    lo = __ffma2_rn(P, h, ot);
+    const float2 hc = __ffma2_rn(P, h, make_float2(-ot.x, -ot.y));   // conj(X[N/2 - k])
+    hi = make_float2(hc.x, -hc.y);
 }
 
 }  // namespace aa
