@@ -41,8 +41,8 @@ def _stale(target: str, deps: list[str]) -> bool:
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
     nvcc = _nvcc()
     extra = []
-    for macro in ("AA_THREADS_PER_SM", "AA_E_BIG", "AA_NTAIL"):          # tuning knobs for experiments: env var -> -D
-        if os.environ.get(macro):
+    for macro in sorted(os.environ):          # tuning knobs for experiments: env var AA_* -> -D
+        if macro.startswith("AA_") and os.environ[macro] != "":
             extra.append(f"-D{macro}={os.environ[macro]}")
             force = True
     objdir = os.path.join(HERE, "build")
