@@ -12,7 +12,12 @@ create call fails with AA_ERR_NO_DEVICE when no sm_100 GPU is visible.
 from ._ffi import (  # noqa: F401
     AAError,
     Analyzer,
+    COND_AGC,
+    COND_CARRY,
+    CondConfig,
+    Conditioner,
     Config,
+    DYNAMICS_DTYPE,
     FEAT_ALL,
     FEAT_CENTROID,
     FEAT_ONSET,

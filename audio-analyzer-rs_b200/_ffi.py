@@ -89,6 +89,29 @@ class Config(C.Structure):
                          noise_floor_db, features)
 
 
+COND_AGC, COND_CARRY = 1, 2
+
+
+class CondConfig(C.Structure):
+    """aa_cond_config (include/aa_gpu.h): the conditioning chain of mod.rs:351-487 + dynamics.rs."""
+    _fields_ = [("sample_rate", C.c_float), ("slot_len", C.c_int32), ("flags", C.c_uint32)]
+
+
+DYNAMICS_DTYPE = np.dtype(
+    [
+        ("level", "<i4"),
+        ("rms_db", "<f4"),
+        ("gain_db", "<f4"),
+        ("session_median_db", "<f4"),
+        ("noise_floor_db", "<f4"),
+        ("effective_gain", "<f4"),
+        ("flags", "<u4"),
+        ("reserved", "<u4"),
+    ]
+)
+assert DYNAMICS_DTYPE.itemsize == 32
+
+
 class _Outputs(C.Structure):
     _fields_ = [
         ("mags", C.c_void_p),
@@ -159,6 +182,12 @@ def lib():
         "aa_yin_host": (i32, [vp, vp, i64, i64, i64, vp, vp]),
         "aa_notes_from_stable_device": (i32, [vp, i64, f32, vp, vp]),
         "aa_notes_from_stable_host": (i32, [vp, i64, f32, vp]),
+        "aa_conditioner_create": (i32, [C.POINTER(CondConfig), pvp]),
+        "aa_conditioner_destroy": (i32, [vp]),
+        "aa_conditioner_reset": (i32, [vp]),
+        "aa_cond_num_slots": (i64, [C.POINTER(CondConfig), i64]),
+        "aa_condition_device": (i32, [vp, vp, i64, i64, i64, vp, vp]),
+        "aa_condition_host": (i32, [vp, vp, i64, i64, i64, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -428,3 +457,43 @@ def yin_device(cfg: YinConfig, clips_ptr: int, n_clips: int, clip_len: int, clip
     _check(lib().aa_yin_device(C.byref(cfg), C.c_void_p(clips_ptr), n_clips, clip_len, clip_stride,
                                C.c_void_p(lag_ptr), C.c_void_p(cmnd_ptr) if cmnd_ptr else None,
                                C.c_void_p(stream) if stream else None))
+
+
+class Conditioner:
+    """Mirror of the reducer thread's per-slot work (mod.rs:431-490): filters, gate, DynamicsTracker."""
+
+    def __init__(self, sample_rate: float, slot_len: int = 1024, agc: bool = True, carry: bool = False):
+        self.cfg = CondConfig(float(sample_rate), int(slot_len), (COND_AGC if agc else 0) | (COND_CARRY if carry else 0))
+        h = C.c_void_p()
+        _check(lib().aa_conditioner_create(C.byref(self.cfg), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().aa_conditioner_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def num_slots(self, clip_len: int) -> int:
+        return int(lib().aa_cond_num_slots(C.byref(self.cfg), int(clip_len)))
+
+    def reset(self):
+        _check(lib().aa_conditioner_reset(self._h))
+
+    def process_host(self, clips: np.ndarray):
+        """Condition [n_clips, clip_len] f32 clips; returns (conditioned copy, dynamics [n_clips, n_slots])."""
+        x = np.ascontiguousarray(np.atleast_2d(clips), np.float32).copy()
+        n_clips, clip_len = x.shape
+        if clip_len % 4:
+            raise ValueError("clip_len must be a multiple of 4 for contiguous clips")
+        dyn = np.zeros((n_clips, self.num_slots(clip_len)), DYNAMICS_DTYPE)
+        _check(lib().aa_condition_host(self._h, _ptr(x), n_clips, clip_len, clip_len,
+                                       _ptr(dyn) if (self.cfg.flags & COND_AGC) else None))
+        return x, dyn
+
+    def process_device(self, clips_ptr: int, n_clips: int, clip_len: int, clip_stride: int, dyn_ptr: int = 0,
+                       stream: int = 0):
+        _check(lib().aa_condition_device(self._h, C.c_void_p(clips_ptr), n_clips, clip_len, clip_stride,
+                                         C.c_void_p(dyn_ptr) if dyn_ptr else None,
+                                         C.c_void_p(stream) if stream else None))

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libaa_gpu.so")
-SOURCES = ["aa_analyze.cu", "aa_fft_batch.cu", "aa_misc.cu", "aa_yin.cu", "aa_api.cu"]
+SOURCES = ["aa_analyze.cu", "aa_fft_batch.cu", "aa_misc.cu", "aa_yin.cu", "aa_cond.cu", "aa_api.cu"]
 HEADERS = ["aa_fft.cuh", "aa_internal.h", os.path.join("..", "..", "include", "aa_gpu.h")]
 
 NVCC_FLAGS = [

@@ -924,3 +924,162 @@ extern "C" AA_API aa_status aa_synth_clips_device(float *clips_dev, int64_t n_cl
     CU(launch_synth(clips_dev, n_clips, clip_len, clip_stride, sample_rate, seed, (cudaStream_t)stream));
     return AA_OK;
 }
+
+// ---------------------------------------------------------------------------
+// input conditioning chain: reducer-thread filters + gate (mod.rs:351-487) and
+// DynamicsTracker (dynamics.rs:156-360)
+// ---------------------------------------------------------------------------
+struct aa_conditioner {
+    aa_cond_config cfg;
+    aa::CondParams p;
+    int device = 0, sms = 0;
+    float *stats = nullptr, *gains = nullptr, *agc_state = nullptr, *carry = nullptr;
+    size_t stats_cap = 0, gains_cap = 0, agc_cap = 0, carry_cap = 0;     // in floats
+    int64_t carry_clips = 0;                                            // clips the carried state belongs to
+};
+
+// mod.rs:357-385, in f32 with the reference's operation order (host libm, like the reference)
+static void calc_biquad(float freq, bool is_lpf, float sample_rate, float out[5])
+{
+    const float PI_F = 3.14159265358979323846f;
+    const float w0 = 2.0f * PI_F * freq / sample_rate;
+    const float cos_w0 = cosf(w0), sin_w0 = sinf(w0);
+    const float alpha = sin_w0 / (2.0f * 0.707f);
+    float b0, b1, b2;
+    if (is_lpf) { b0 = (1.0f - cos_w0) / 2.0f; b1 = 1.0f - cos_w0; b2 = (1.0f - cos_w0) / 2.0f; }
+    else        { b0 = (1.0f + cos_w0) / 2.0f; b1 = -(1.0f + cos_w0); b2 = (1.0f + cos_w0) / 2.0f; }
+    const float a0 = 1.0f + alpha, a1 = -2.0f * cos_w0, a2 = 1.0f - alpha;
+    out[0] = b0 / a0; out[1] = b1 / a0; out[2] = b2 / a0; out[3] = a1 / a0; out[4] = a2 / a0;
+}
+
+extern "C" AA_API int64_t aa_cond_num_slots(const aa_cond_config *cfg, int64_t clip_len)
+{
+    if (!cfg || cfg->slot_len <= 0 || clip_len < 0) return 0;
+    return clip_len / cfg->slot_len;
+}
+
+extern "C" AA_API aa_status aa_conditioner_create(const aa_cond_config *cfg, aa_conditioner **out)
+{
+    if (!cfg || !out) return fail(AA_ERR_INVALID, "aa_conditioner_create: null argument");
+    *out = nullptr;
+    if (!(cfg->sample_rate > 0.0f) || cfg->slot_len < 4 || (cfg->slot_len & 3))
+        return fail(AA_ERR_INVALID, "aa_conditioner_create: sample_rate must be > 0 and slot_len a positive multiple of 4");
+    int sms = 0;
+    aa_status st = check_device(&sms);
+    if (st != AA_OK) return st;
+    aa_conditioner *h = new (std::nothrow) aa_conditioner();
+    if (!h) return fail(AA_ERR_INVALID, "out of host memory");
+    h->cfg = *cfg;
+    h->device = g_device;
+    h->sms = sms;
+    aa::CondParams &p = h->p;
+    const float sr = cfg->sample_rate;
+    calc_biquad(40.0f, false, sr, p.hp);                                   // mod.rs:387
+    calc_biquad(14000.0f, true, sr, p.lp);                                 // mod.rs:388
+    p.gate_threshold_linear = powf(10.0f, -60.0f / 20.0f);                 // mod.rs:400-401
+    p.release_coeff = expf(-1.0f / (0.040f * sr));                         // mod.rs:408
+    p.gate_hold_samples = (int32_t)(0.020f * sr);                          // mod.rs:413
+    const float slot_rate = sr / (float)cfg->slot_len;                     // dynamics.rs:164
+    p.target_db = -18.0f;                                                  // mod.rs:347-355
+    p.max_boost_db = 100.0f;
+    p.smooth_alpha = 1.0f - expf(-1.0f / (240.0f * slot_rate));            // dynamics.rs:174
+    p.silence_decay_alpha = 1.0f - expf(-1.0f / (10.0f * slot_rate));      // dynamics.rs:175
+    p.active_snr_db = 20.0f;                                               // dynamics.rs:188
+    p.bootstrap_floor_db = -55.0f;                                         // dynamics.rs:189
+    p.slot_len = cfg->slot_len;
+    *out = h;
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_conditioner_destroy(aa_conditioner *h)
+{
+    if (!h) return AA_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->stats); cudaFree(h->gains); cudaFree(h->agc_state); cudaFree(h->carry);
+    delete h;
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_conditioner_reset(aa_conditioner *h)
+{
+    if (!h) return fail(AA_ERR_INVALID, "aa_conditioner_reset: null handle");
+    h->carry_clips = 0;       // the next call re-initialises the carried state
+    return AA_OK;
+}
+
+static aa_status cond_grow(float **buf, size_t *cap, size_t need)
+{
+    if (*cap >= need) return AA_OK;
+    cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    CU(cudaMalloc(buf, need * sizeof(float)));
+    *cap = need;
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_condition_device(aa_conditioner *h, float *clips_dev, int64_t n_clips, int64_t clip_len,
+                                                int64_t clip_stride, aa_dynamics *dyn_dev, void *stream)
+{
+    if (!h || !clips_dev) return fail(AA_ERR_INVALID, "aa_condition_device: null argument");
+    if (n_clips < 0 || clip_len < 0 || clip_stride < 0 || (clip_stride & 3) || (reinterpret_cast<uintptr_t>(clips_dev) & 15))
+        return fail(AA_ERR_INVALID, "aa_condition_device: clips must be 16-byte aligned with clip_stride % 4 == 0");
+    if (n_clips > 1 && clip_stride < clip_len)
+        return fail(AA_ERR_INVALID, "aa_condition_device: overlapping clips cannot be conditioned in place");
+    const int64_t n_slots = clip_len / h->cfg.slot_len;
+    if (n_clips == 0 || n_slots == 0) return AA_OK;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool agc = (h->cfg.flags & AA_COND_AGC) != 0;
+    const bool carry = (h->cfg.flags & AA_COND_CARRY) != 0;
+    aa_status st;
+    if (carry) {
+        if ((st = cond_grow(&h->carry, &h->carry_cap, (size_t)n_clips * 16)) != AA_OK) return st;
+        if (h->carry_clips != n_clips) {     // first use (or a different batch shape): start from the initial state
+            CU(cudaMemsetAsync(h->carry, 0, (size_t)n_clips * 16 * sizeof(float), s));
+        }
+    }
+    if (agc) {
+        const size_t per = aa::cond_agc_state_floats();
+        if ((st = cond_grow(&h->stats, &h->stats_cap, (size_t)(n_clips * n_slots) * 4)) != AA_OK) return st;
+        if ((st = cond_grow(&h->gains, &h->gains_cap, (size_t)(n_clips * n_slots))) != AA_OK) return st;
+        const size_t old_cap = h->agc_cap;
+        if ((st = cond_grow(&h->agc_state, &h->agc_cap, (size_t)n_clips * per)) != AA_OK) return st;
+        if (carry && (h->carry_clips != n_clips || old_cap != h->agc_cap))   // scalars (incl. the valid mark) to zero
+            CU(cudaMemsetAsync(h->agc_state, 0, (size_t)n_clips * per * sizeof(float), s));
+    }
+    if (carry) h->carry_clips = n_clips;
+    CU(aa::launch_cond_filter_gate(clips_dev, n_clips, clip_stride, n_slots, h->p, agc ? h->stats : nullptr,
+                                   carry ? h->carry : nullptr, s));
+    if (agc) {
+        CU(aa::launch_cond_agc(h->stats, n_clips, n_slots, h->p, h->agc_state, carry ? 1 : 0, h->gains, dyn_dev, s));
+        CU(aa::launch_cond_apply_gain(clips_dev, n_clips, clip_stride, n_slots, h->cfg.slot_len, h->gains, h->sms, s));
+    }
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_condition_host(aa_conditioner *h, float *clips_host, int64_t n_clips, int64_t clip_len,
+                                              int64_t clip_stride, aa_dynamics *dyn_host)
+{
+    if (!h || !clips_host) return fail(AA_ERR_INVALID, "aa_condition_host: null argument");
+    if (n_clips < 0 || clip_len < 0 || clip_stride < 0 || (clip_stride & 3))
+        return fail(AA_ERR_INVALID, "aa_condition_host: clip_stride must be a non-negative multiple of 4");
+    const int64_t n_slots = clip_len / h->cfg.slot_len;
+    if (n_clips == 0 || n_slots == 0) return AA_OK;
+    CU(cudaSetDevice(h->device));
+    const size_t span = (size_t)((n_clips - 1) * clip_stride + clip_len);
+    const size_t nd = (size_t)(n_clips * n_slots);
+    float *d = nullptr;
+    aa_dynamics *dd = nullptr;
+    cudaError_t e = cudaMalloc(&d, span * sizeof(float));
+    if (e == cudaSuccess && dyn_host && (h->cfg.flags & AA_COND_AGC)) e = cudaMalloc(&dd, nd * sizeof(aa_dynamics));
+    if (e == cudaSuccess) e = cudaMemcpy(d, clips_host, span * sizeof(float), cudaMemcpyHostToDevice);
+    aa_status st = AA_OK;
+    if (e == cudaSuccess) st = aa_condition_device(h, d, n_clips, clip_len, clip_stride, dd, nullptr);
+    if (e == cudaSuccess && st == AA_OK) e = cudaMemcpy(clips_host, d, span * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && st == AA_OK && dd) e = cudaMemcpy(dyn_host, dd, nd * sizeof(aa_dynamics), cudaMemcpyDeviceToHost);
+    cudaFree(d); cudaFree(dd);
+    if (st != AA_OK) return st;
+    if (e != cudaSuccess) return fail_cuda(e, "aa_condition_host");
+    return AA_OK;
+}

@@ -63,6 +63,23 @@ cudaError_t launch_yin(const float *clips, int64_t n_clips, int64_t clip_stride,
                        int num_sms, cudaStream_t s);
 cudaError_t launch_notes(const aa_stable_pitches *stable, int64_t n_frames, float base_c0,
                          aa_note_record *out, cudaStream_t s);
+// Conditioning chain (aa_cond.cu).  Coefficients are computed on the host with the reference's own f32 formulas
+// (mod.rs:357-418, dynamics.rs:164-189) so that the device arithmetic starts from identical bits.
+struct CondParams {
+    float hp[5], lp[5];              // b0 b1 b2 a1 a2, normalised by a0
+    float gate_threshold_linear, release_coeff;
+    int32_t gate_hold_samples;
+    float target_db, max_boost_db, smooth_alpha, silence_decay_alpha, active_snr_db, bootstrap_floor_db;
+    int32_t slot_len;
+};
+size_t      cond_agc_state_floats();
+cudaError_t launch_cond_filter_gate(float *clips, int64_t n_clips, int64_t clip_stride, int64_t n_slots,
+                                    const CondParams &p, float *stats, float *carry, cudaStream_t s);
+cudaError_t launch_cond_agc(const float *stats, int64_t n_clips, int64_t n_slots, const CondParams &p, float *state,
+                            int carry, float *gains, aa_dynamics *dyn, cudaStream_t s);
+cudaError_t launch_cond_apply_gain(float *clips, int64_t n_clips, int64_t clip_stride, int64_t n_slots, int slot_len,
+                                   const float *gains, int num_sms, cudaStream_t s);
+
 cudaError_t launch_synth(float *clips, int64_t n_clips, int64_t clip_len, int64_t clip_stride,
                          float sample_rate, uint64_t seed, cudaStream_t s);
 

@@ -244,6 +244,42 @@ AA_API aa_status aa_stream_poll(aa_stream *h, aa_stream_frame *out, int32_t max,
 AA_API aa_status aa_stream_reset(aa_stream *h);
 
 /* ------------------------------------------------------------------------- *
+ * Input conditioning chain (the step right before the analysis path).
+ * Replaces the body of the reducer thread in AudioPipeline (src/audio_io/mod.rs:351-487:
+ * 40 Hz high-pass and 14 kHz low-pass biquads, envelope follower, -60 dBFS gate with 20 ms hold)
+ * and DynamicsTracker::process_slot (src/audio_io/dynamics.rs:194-360: slot RMS, noise-floor /
+ * session percentiles, AGC gain smoothing with peak headroom, dynamics classification), slot by
+ * slot (slot_len samples, 1024 in the reference: mod.rs:126-128).  Clips are conditioned in place;
+ * only full slots exist in the reference (mod.rs:799-803), so samples after the last full slot of a
+ * clip are left untouched.  aa_dynamics mirrors DynamicsOutput (dynamics.rs:78-91); its
+ * noise_floor_db is what STFT / OnsetDetector read every frame (stft.rs:322, onset.rs:300).
+ * ------------------------------------------------------------------------- */
+#define AA_COND_AGC   1u   /* run DynamicsTracker (AGC + classification); otherwise filters + gate only */
+#define AA_COND_CARRY 2u   /* keep filter / gate / tracker state in the handle between calls (streams) */
+typedef struct aa_cond_config {
+    float    sample_rate;
+    int32_t  slot_len;     /* samples per slot, multiple of 4 (1024 in the reference) */
+    uint32_t flags;        /* AA_COND_* */
+} aa_cond_config;
+typedef struct aa_dynamics {             /* 32 bytes, one per slot */
+    int32_t  level;                      /* DynamicLevel: 0 Silence, 1 ppp, 2 pp, 3 p, 4 mp, 5 mf, 6 f, 7 ff, 8 fff */
+    float    rms_db, gain_db, session_median_db, noise_floor_db;   /* dynamics.rs:83-90 */
+    float    effective_gain;             /* linear gain applied to the slot (dynamics.rs:327-328) */
+    uint32_t flags;                      /* 1 is_active, 2 is_broadband, 4 is_playing */
+    uint32_t reserved;
+} aa_dynamics;
+typedef struct aa_conditioner aa_conditioner;
+AA_API aa_status aa_conditioner_create(const aa_cond_config *cfg, aa_conditioner **out);
+AA_API aa_status aa_conditioner_destroy(aa_conditioner *h);
+AA_API aa_status aa_conditioner_reset(aa_conditioner *h);           /* forget carried state */
+AA_API int64_t   aa_cond_num_slots(const aa_cond_config *cfg, int64_t clip_len);
+/* clip c at clips + c*clip_stride (clip_stride % 4 == 0, base 16-byte aligned); dyn: [n_clips][num_slots] or NULL */
+AA_API aa_status aa_condition_device(aa_conditioner *h, float *clips_dev, int64_t n_clips, int64_t clip_len,
+                                     int64_t clip_stride, aa_dynamics *dyn_dev, void *stream);
+AA_API aa_status aa_condition_host(aa_conditioner *h, float *clips_host, int64_t n_clips, int64_t clip_len,
+                                   int64_t clip_stride, aa_dynamics *dyn_host);
+
+/* ------------------------------------------------------------------------- *
  * Synthetic clips (bench/test support): clip c = K = 1..4 harmonic
  * tones (6 partials, 1/h amplitudes, f0 log-uniform in [55,1760] Hz) plus white
  * noise at -60 dBFS, all derived from splitmix64(seed + c).

@@ -186,6 +186,38 @@ int64_t aao_analyze_batch(const aao_config *cfg, const float *clips, int64_t n_c
                           int64_t clip_len, int n_threads, float *mags_out,
                           aao_features *feat_out, aao_stable *stable_out);
 
+/* ---- input conditioning chain: aa_oracle_cond.c ------------------------
+ * Reducer-thread HPF / LPF biquads + envelope gate (mod.rs:351-487) and
+ * DynamicsTracker::process_slot (dynamics.rs:194-360). */
+typedef struct aao_cond_params {
+    float   hp[5], lp[5];            /* b0 b1 b2 a1 a2, normalised by a0   mod.rs:357-388 */
+    float   gate_threshold_linear;   /* 10^(-60/20)                         mod.rs:401 */
+    float   release_coeff;           /* exp(-1/(0.040 sr))                  mod.rs:408 */
+    int32_t gate_hold_samples;       /* (0.020 sr) as usize                 mod.rs:413 */
+    float   target_db, max_boost_db, smooth_alpha, silence_decay_alpha;   /* dynamics.rs:156-186 */
+    float   active_snr_db, bootstrap_floor_db;                            /* dynamics.rs:188-189 */
+    int32_t slot_len;                /* samples per slot (mod.rs: 1024) */
+} aao_cond_params;
+
+/* DynamicsOutput (dynamics.rs:78-91) of one slot + the gain that was applied; 32 bytes, identical
+ * layout to aa_dynamics.  level: 0 Silence, 1 ppp, 2 pp, 3 p, 4 mp, 5 mf, 6 f, 7 ff, 8 fff. */
+typedef struct aao_dynamics {
+    int32_t  level;
+    float    rms_db, gain_db, session_median_db, noise_floor_db;
+    float    effective_gain;         /* min(current_gain_linear, 0.97 / peak)  dynamics.rs:327-328 */
+    uint32_t flags;                  /* 1 is_active, 2 is_broadband, 4 is_playing */
+    uint32_t reserved;
+} aao_dynamics;
+
+typedef struct aao_cond aao_cond;
+void      aao_cond_params_init(aao_cond_params *p, float sample_rate, int slot_len);
+aao_cond *aao_cond_create(const aao_cond_params *p);
+void      aao_cond_destroy(aao_cond *c);
+void      aao_cond_reset(aao_cond *c);
+void      aao_cond_filter_gate(aao_cond *c, float *slot, int len);
+void      aao_cond_agc(aao_cond *c, float *slot, int len, aao_dynamics *out, int apply);
+int64_t   aao_cond_clip(const aao_cond_params *p, float *samples, int64_t len, aao_dynamics *dyn, int agc);
+
 #ifdef __cplusplus
 }
 #endif

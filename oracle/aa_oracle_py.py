@@ -69,6 +69,39 @@ class Config(C.Structure):
     ]
 
 
+class CondParams(C.Structure):
+    """aao_cond_params (aa_oracle.h): coefficients of the conditioning chain."""
+    _fields_ = [
+        ("hp", C.c_float * 5),
+        ("lp", C.c_float * 5),
+        ("gate_threshold_linear", C.c_float),
+        ("release_coeff", C.c_float),
+        ("gate_hold_samples", C.c_int32),
+        ("target_db", C.c_float),
+        ("max_boost_db", C.c_float),
+        ("smooth_alpha", C.c_float),
+        ("silence_decay_alpha", C.c_float),
+        ("active_snr_db", C.c_float),
+        ("bootstrap_floor_db", C.c_float),
+        ("slot_len", C.c_int32),
+    ]
+
+
+DYNAMICS_DTYPE = np.dtype(
+    [
+        ("level", "<i4"),
+        ("rms_db", "<f4"),
+        ("gain_db", "<f4"),
+        ("session_median_db", "<f4"),
+        ("noise_floor_db", "<f4"),
+        ("effective_gain", "<f4"),
+        ("flags", "<u4"),
+        ("reserved", "<u4"),
+    ]
+)
+assert DYNAMICS_DTYPE.itemsize == 32
+
+
 def make_config(n=2048, hop=512, sample_rate=44100.0, min_freq=24.0, max_freq=10000.0,
                 noise_floor_db=-96.0, features=FEAT_PITCH | FEAT_ONSET | FEAT_CENTROID | FEAT_TRACKER):
     return Config(n, hop, sample_rate, min_freq, max_freq, noise_floor_db, features)
@@ -76,11 +109,8 @@ def make_config(n=2048, hop=512, sample_rate=44100.0, min_freq=24.0, max_freq=10
 
 def build(force: bool = False) -> str:
     """Compile oracle/aa_oracle.c -> oracle/libaa_oracle.so (gcc)."""
-    src = os.path.join(_HERE, "aa_oracle.c")
-    hdr = os.path.join(_HERE, "aa_oracle.h")
-    stale = (not os.path.exists(_SO)) or any(
-        os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr)
-    )
+    srcs = [os.path.join(_HERE, f) for f in ("aa_oracle.c", "aa_oracle_cond.c", "aa_oracle.h")]
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(p) > os.path.getmtime(_SO) for p in srcs)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B", "libaa_oracle.so"],
                               stdout=subprocess.DEVNULL)
@@ -137,6 +167,9 @@ def lib():
     L.aao_analyze_clip.argtypes = [C.POINTER(Config), fp, C.c_int64, fp, u8p, fp, fp, u8p, vp, vp, vp]
     L.aao_analyze_batch.restype = C.c_int64
     L.aao_analyze_batch.argtypes = [C.POINTER(Config), fp, C.c_int64, C.c_int64, C.c_int, fp, vp, vp]
+    L.aao_cond_params_init.argtypes = [C.POINTER(CondParams), C.c_float, C.c_int]
+    L.aao_cond_clip.restype = C.c_int64
+    L.aao_cond_clip.argtypes = [C.POINTER(CondParams), fp, C.c_int64, vp, C.c_int]
     _lib = L
     return L
 
@@ -326,3 +359,21 @@ def analyze_batch(cfg: Config, clips: np.ndarray, n_threads: int, want_mags=Fals
                                     _fp(mags), _vp(feat), _vp(stable))
     assert total == T * n_clips
     return {"T": T, "mags": mags, "features": feat, "stable": stable}
+
+
+def cond_params(sample_rate: float, slot_len: int = 1024) -> CondParams:
+    p = CondParams()
+    lib().aao_cond_params_init(C.byref(p), float(sample_rate), int(slot_len))
+    return p
+
+
+def condition_clip(samples: np.ndarray, sample_rate: float, slot_len: int = 1024, agc: bool = True):
+    """Reference conditioning chain (mod.rs:351-487 + dynamics.rs:194-360) over one clip.
+    Returns (conditioned samples, per-slot dynamics records)."""
+    x = np.ascontiguousarray(samples, dtype=np.float32).copy()
+    p = cond_params(sample_rate, slot_len)
+    n_slots = len(x) // slot_len
+    dyn = np.zeros(n_slots, dtype=DYNAMICS_DTYPE)
+    got = lib().aao_cond_clip(C.byref(p), _fp(x), len(x), _vp(dyn), 1 if agc else 0)
+    assert got == n_slots
+    return x, dyn

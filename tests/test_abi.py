@@ -87,3 +87,16 @@ def test_product_does_not_import_the_oracle():
         if os.path.isfile(path) and path.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
             text = open(path, errors="ignore").read()
             assert "aa_oracle" not in text and "oracle/" not in text, path
+
+
+def test_conditioner_boundary(aa, O):
+    """aa_cond_config / aa_dynamics layouts and host-side argument checks (no GPU needed)."""
+    assert C.sizeof(aa.CondConfig) == 12
+    assert aa.DYNAMICS_DTYPE.itemsize == 32 and aa.DYNAMICS_DTYPE == O.DYNAMICS_DTYPE
+    cfg = aa.CondConfig(48000.0, 1024, aa.COND_AGC)
+    assert aa.lib().aa_cond_num_slots(C.byref(cfg), 1440000) == 1406
+    assert aa.lib().aa_cond_num_slots(C.byref(cfg), 1023) == 0
+    for bad in [(48000.0, 1023), (48000.0, 0), (0.0, 1024)]:
+        with pytest.raises(aa.AAError) as e:
+            aa.Conditioner(*bad)
+        assert e.value.code == -1
