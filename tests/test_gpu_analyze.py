@@ -183,6 +183,28 @@ def test_noise_floor_db_and_freq_range_parameters(aa, O, torch_cuda):
         assert len(bad) == 0
 
 
+@pytest.mark.parametrize("n,sr", [(4096, 48000.0), (2048, 44100.0), (1024, 48000.0), (256, 48000.0)])
+def test_production_kernel_variants_equal_the_tap_build(aa, O, torch_cuda, n, sr):
+    """The parity checks above run the instantiation with the debug taps, which keeps every bin's floor state.
+    The production instantiations drop the pitch-floor recurrence of bin groups above max_bin (dead state) and
+    are templated on how many group slots per warp can be live: max_freq picks the variant (few live slots /
+    all slots).  Every record must be byte-identical to the tap build, and the tap build is checked against
+    the oracle for the same parameters."""
+    clips = np.stack([signals.multitone(300 + i, sr, 24 * n) for i in range(5)])
+    clips[4] *= 0.0
+    for fmax in (900.0, 10000.0, 20000.0):
+        cfg = aa.Config(n=n, sample_rate=sr, max_freq=fmax)
+        tap = aa.Analyzer(cfg).analyze_host(clips, want_dbg=True)
+        prod = aa.Analyzer(cfg).analyze_host(clips, want_dbg=False)
+        for k in ("features", "stable", "mags", "summaries"):
+            assert tap[k].tobytes() == prod[k].tobytes(), f"n={n} max_freq={fmax}: {k} differs"
+        ocfg = O.make_config(n, n // 4, sr, 24.0, fmax, -96.0)
+        iso = O.analyze_clip(ocfg, mags_in=tap["mags"][0], want_floor=True, want_peaks=True, want_diag=True)
+        assert np.array_equal(tap["dbg_floor"][0], iso["floor"]) and np.array_equal(tap["dbg_peaks"][0], iso["peaks"])
+        bad, _ = util.compare_pitch_records(prod["features"][0], iso["features"], iso["diag"])
+        assert len(bad) == 0
+
+
 def test_onset_in_drives_the_tracker(aa, O, torch_cuda):
     x = signals.multitone(33, 44100.0, 60000)[None, :]
     T = (60000 - 2048) // 512 + 1
