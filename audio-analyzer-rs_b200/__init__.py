@@ -36,6 +36,9 @@ from ._ffi import (  # noqa: F401
     STREAM_FRAME_DTYPE,
     SUMMARY_DTYPE,
     Stream,
+    TUNER_RECORD_DTYPE,
+    INT_TYPES,
+    tuner_from_stable,
     YinConfig,
     device_count,
     exported_symbols,

@@ -182,6 +182,8 @@ def lib():
         "aa_yin_host": (i32, [vp, vp, i64, i64, i64, vp, vp]),
         "aa_notes_from_stable_device": (i32, [vp, i64, f32, vp, vp]),
         "aa_notes_from_stable_host": (i32, [vp, i64, f32, vp]),
+        "aa_tuner_from_stable_device": (i32, [vp, i64, f32, i32, i32, vp, vp]),
+        "aa_tuner_from_stable_host": (i32, [vp, i64, f32, i32, i32, vp]),
         "aa_conditioner_create": (i32, [C.POINTER(CondConfig), pvp]),
         "aa_conditioner_destroy": (i32, [vp]),
         "aa_conditioner_reset": (i32, [vp]),
@@ -497,3 +499,21 @@ class Conditioner:
         _check(lib().aa_condition_device(self._h, C.c_void_p(clips_ptr), n_clips, clip_len, clip_stride,
                                          C.c_void_p(dyn_ptr) if dyn_ptr else None,
                                          C.c_void_p(stream) if stream else None))
+
+
+TUNER_RECORD_DTYPE = np.dtype(
+    [("kind", "u1"), ("best", "u1"), ("lo", "u1"), ("hi", "u1"), ("interval", "<u4"), ("accuracy", "<f4"), ("cents", "<f4")]
+)
+assert TUNER_RECORD_DTYPE.itemsize == 16
+INT_TYPES = ["Min2", "Maj2", "Min3", "Maj3", "Per4", "Aug4", "Per5", "Min6", "Maj6", "Min7", "Maj7", "Per8"]
+SYSTEM_EQUAL, SYSTEM_JUST, SYSTEM_PYTHAGOREAN = 0, 1, 2
+
+
+def tuner_from_stable(stable: np.ndarray, base_freq: float = 440.0, system: int = 0,
+                      single_pitch_mode: bool = False) -> np.ndarray:
+    """Tuner::run's per-frame branch + Interval::new (tuner.rs:148-193, theory.rs:306-382) on stable pitches."""
+    st = np.ascontiguousarray(stable, STABLE_DTYPE).reshape(-1)
+    out = np.zeros(st.shape[0], TUNER_RECORD_DTYPE)
+    _check(lib().aa_tuner_from_stable_host(_ptr(st), st.shape[0], float(base_freq), int(system),
+                                           1 if single_pitch_mode else 0, _ptr(out)))
+    return out.reshape(np.shape(stable))

@@ -1083,3 +1083,42 @@ extern "C" AA_API aa_status aa_condition_host(aa_conditioner *h, float *clips_ho
     if (e != cudaSuccess) return fail_cuda(e, "aa_condition_host");
     return AA_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Tuner::run per-frame branch + Interval::new: tuner.rs:148-193, theory.rs:306-382
+// ---------------------------------------------------------------------------
+extern "C" AA_API aa_status aa_tuner_from_stable_device(const aa_stable_pitches *stable_dev, int64_t n_frames,
+                                                        float base_freq, int32_t system, int32_t single_pitch_mode,
+                                                        aa_tuner_record *out_dev, void *stream)
+{
+    if (!stable_dev || !out_dev || n_frames < 0 || !(base_freq > 0.0f) || system < 0 || system > 2)
+        return fail(AA_ERR_INVALID, "aa_tuner_from_stable_device: bad argument (system is 0, 1 or 2)");
+    aa_status st = check_device(nullptr);
+    if (st != AA_OK) return st;
+    CU(launch_tuner(stable_dev, n_frames, base_freq * powf(2.0f, -4.75f), system, single_pitch_mode ? 1 : 0, out_dev,
+                    (cudaStream_t)stream));
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_tuner_from_stable_host(const aa_stable_pitches *stable_host, int64_t n_frames,
+                                                      float base_freq, int32_t system, int32_t single_pitch_mode,
+                                                      aa_tuner_record *out_host)
+{
+    if (!stable_host || !out_host || n_frames < 0 || !(base_freq > 0.0f) || system < 0 || system > 2)
+        return fail(AA_ERR_INVALID, "aa_tuner_from_stable_host: bad argument (system is 0, 1 or 2)");
+    if (n_frames == 0) return AA_OK;
+    aa_status st = check_device(nullptr);
+    if (st != AA_OK) return st;
+    aa_stable_pitches *d_in = nullptr;
+    aa_tuner_record *d_out = nullptr;
+    CU(cudaMalloc(&d_in, sizeof(aa_stable_pitches) * (size_t)n_frames));
+    cudaError_t e = cudaMalloc(&d_out, sizeof(aa_tuner_record) * (size_t)n_frames);
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, stable_host, sizeof(aa_stable_pitches) * (size_t)n_frames, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = launch_tuner(d_in, n_frames, base_freq * powf(2.0f, -4.75f), system, single_pitch_mode ? 1 : 0, d_out, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(out_host, d_out, sizeof(aa_tuner_record) * (size_t)n_frames, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail_cuda(e, "aa_tuner_from_stable_host");
+    return AA_OK;
+}

@@ -101,6 +101,76 @@ cudaError_t launch_notes(const aa_stable_pitches *stable, int64_t n_frames, floa
 }
 
 // ---------------------------------------------------------------------------
+// Tuner::run's per-frame branch (reference src/analysis/tuner.rs:148-193) and Interval::new
+// (src/analysis/theory.rs:306-382) on the stable pitches of every frame: which note is displayed, or which
+// interval lies between the two notes and how far off it is.  One thread per frame.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float note_cents(float freq, float base_c0)
+{
+    const float lg = __fmul_rn(log2f(__fdiv_rn(freq, base_c0)), 1200.0f);              // theory.rs:198
+    const float c = fmodf(lg, 100.0f);                                                  // :201
+    return c < 50.0f ? c : -__fsub_rn(100.0f, c);                                       // :202-206
+}
+
+__global__ void __launch_bounds__(256) tuner_kernel(const aa_stable_pitches *__restrict__ stable, int64_t n_frames,
+                                                    float base_c0, int system, int single_pitch_mode,
+                                                    aa_tuner_record *__restrict__ out)
+{
+    // theory.rs:317-352 (f32 constant expressions fold with the same rounding as in Rust)
+    const float JUST[13] = {1.0f, 16.0f / 15.0f, 9.0f / 8.0f, 6.0f / 5.0f, 5.0f / 4.0f, 4.0f / 3.0f, 45.0f / 32.0f,
+                            3.0f / 2.0f, 8.0f / 5.0f, 5.0f / 3.0f, 9.0f / 5.0f, 15.0f / 8.0f, 2.0f};
+    const float PYTH[13] = {1.0f, 256.0f / 243.0f, 9.0f / 8.0f, 32.0f / 27.0f, 81.0f / 64.0f, 4.0f / 3.0f, 729.0f / 512.0f,
+                            3.0f / 2.0f, 128.0f / 81.0f, 27.0f / 16.0f, 32.0f / 9.0f, 243.0f / 128.0f, 2.0f};
+    const float ET[13] = {1.0f, 1.0595f, 1.1225f, 1.1892f, 1.2599f, 1.3348f, 1.4142f, 1.4983f, 1.5874f, 1.6818f,
+                          1.7818f, 1.8877f, 2.0f};
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    const aa_stable_pitches &sp = stable[f];
+    const int n = (int)min(sp.n, (uint32_t)AA_MAX_STABLE);
+    aa_tuner_record r;
+    r.kind = 0; r.best = 0; r.lo = 0; r.hi = 0; r.interval = 0u; r.accuracy = 0.0f; r.cents = 0.0f;
+    if (n == 1 || (n > 0 && single_pitch_mode)) {
+        int b = 0;                                             // Iterator::max_by: the last maximum
+        for (int i = 1; i < n; ++i)
+            if (!(sp.pitch[i].score < sp.pitch[b].score)) b = i;
+        r.kind = 1; r.best = (uint8_t)b;
+        r.cents = note_cents(sp.pitch[b].freq, base_c0);       // tuner.rs:163-165
+    } else if (n == 2) {
+        const int l = sp.pitch[1].freq < sp.pitch[0].freq ? 1 : 0;   // tuner.rs:169-170
+        const float f_lo = sp.pitch[l].freq, f_hi = sp.pitch[1 - l].freq;
+        r.kind = 2; r.lo = (uint8_t)l; r.hi = (uint8_t)(1 - l);
+        if (f_lo == 0.0f) {                                    // theory.rs:307-312
+            r.interval = 11u;
+        } else {
+            float ratio = __fdiv_rn(f_hi, f_lo);
+            while (ratio > 2.0f) ratio = __fdiv_rn(ratio, 2.0f);
+            const float *tab = system == 1 ? JUST : system == 2 ? PYTH : ET;
+            int idx = 0;
+            float best = fabsf(__fsub_rn(ratio, tab[0]));
+            for (int i = 1; i < 13; ++i) {                     // min_by: the first minimum
+                const float d = fabsf(__fsub_rn(ratio, tab[i]));
+                if (d < best) { best = d; idx = i; }
+            }
+            r.interval = idx == 0 ? 11u : (uint32_t)(idx - 1);
+            r.accuracy = __fmul_rn(-logf(__fdiv_rn(tab[idx], ratio)), 1732.5f);     // theory.rs:381
+        }
+        r.cents = r.accuracy;                                  // tuner.rs:181
+    } else if (n >= 3) {
+        r.kind = 3;                                            // tuner.rs:183-189: names only
+    }
+    out[f] = r;
+}
+
+cudaError_t launch_tuner(const aa_stable_pitches *stable, int64_t n_frames, float base_c0, int system,
+                         int single_pitch_mode, aa_tuner_record *out, cudaStream_t s)
+{
+    if (n_frames <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n_frames + 255) / 256);
+    tuner_kernel<<<grid, 256, 0, s>>>(stable, n_frames, base_c0, system, single_pitch_mode, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // Synthetic clips.
 // ---------------------------------------------------------------------------
 __host__ __device__ inline uint64_t splitmix64(uint64_t &x)

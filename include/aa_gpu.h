@@ -200,6 +200,25 @@ AA_API aa_status aa_notes_from_stable_device(const aa_stable_pitches *stable_dev
 AA_API aa_status aa_notes_from_stable_host(const aa_stable_pitches *stable_host, int64_t n_frames,
                                            float base_freq, aa_note_record *notes_host);
 
+/* Tuner::run's per-frame branch (src/analysis/tuner.rs:148-193) with Interval::new
+ * (src/analysis/theory.rs:306-382) on the stable pitches: numeric form of TunerOutput.label / .cents
+ * (the strings stay on the host).  system: 0 EqualTemperament, 1 JustIntonation, 2 Pythagorean
+ * (tuner.rs:13-18); single_pitch_mode: TunerMode::SinglePitch (tuner.rs:21-25). */
+typedef struct aa_tuner_record {          /* 16 bytes, one per frame, parallel to aa_stable_pitches */
+    uint8_t  kind;      /* 0 nothing emitted (no stable pitch), 1 single note, 2 interval, 3 three or more notes */
+    uint8_t  best;      /* kind 1: index of the displayed pitch (highest score; the last one on ties) */
+    uint8_t  lo, hi;    /* kind 2: indices of the lower / higher pitch */
+    uint32_t interval;  /* kind 2: IntType 0 Min2, 1 Maj2, 2 Min3, 3 Maj3, 4 Per4, 5 Aug4, 6 Per5, 7 Min6, 8 Maj6,
+                           9 Min7, 10 Maj7, 11 Per8 (theory.rs:285-298) */
+    float    accuracy;  /* kind 2: Interval::get_accuracy() */
+    float    cents;     /* TunerOutput.cents: note cents (kind 1), interval accuracy (kind 2), 0 otherwise */
+} aa_tuner_record;
+AA_API aa_status aa_tuner_from_stable_device(const aa_stable_pitches *stable_dev, int64_t n_frames, float base_freq,
+                                             int32_t system, int32_t single_pitch_mode,
+                                             aa_tuner_record *out_dev, void *stream);
+AA_API aa_status aa_tuner_from_stable_host(const aa_stable_pitches *stable_host, int64_t n_frames, float base_freq,
+                                           int32_t system, int32_t single_pitch_mode, aa_tuner_record *out_host);
+
 /* ------------------------------------------------------------------------- *
  * YIN-style lag search per frame (NEW, no reference code; the north_star asks
  * for "autocorrelation or YIN-style lag search").  On the raw (unwindowed) frame

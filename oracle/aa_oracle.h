@@ -216,6 +216,9 @@ void      aao_cond_destroy(aao_cond *c);
 void      aao_cond_reset(aao_cond *c);
 void      aao_cond_filter_gate(aao_cond *c, float *slot, int len);
 void      aao_cond_agc(aao_cond *c, float *slot, int len, aao_dynamics *out, int apply);
+int       aao_interval(float f_lo, float f_hi, int system, float *accuracy);
+void      aao_tuner_frame(const float *pairs, int n, int system, int single_pitch_mode, int *kind, int *best, int *lo,
+                          int *hi, int *interval, float *accuracy);
 int64_t   aao_cond_clip(const aao_cond_params *p, float *samples, int64_t len, aao_dynamics *dyn, int agc);
 
 #ifdef __cplusplus

@@ -262,3 +262,55 @@ int64_t aao_cond_clip(const aao_cond_params *p, float *samples, int64_t len, aao
     aao_cond_destroy(c);
     return n_slots;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Tuner post-stage: Interval::new (src/analysis/theory.rs:306-382) and the
+ * mode selection of Tuner::run (src/analysis/tuner.rs:152-193).  PINNED by the reference's own
+ * known-answer tests (theory.rs:545-604), which tests/test_oracle_cond.py replays.
+ * system: 0 EqualTemperament (default), 1 JustIntonation, 2 Pythagorean (tuner.rs:13-18).
+ * Returns the IntType index 0 Min2 .. 10 Maj7, 11 Per8 (theory.rs:285-298). */
+int aao_interval(float f_lo, float f_hi, int system, float *accuracy)
+{
+    static const float JUST[13] = {1.0f, 16.0f / 15.0f, 9.0f / 8.0f, 6.0f / 5.0f, 5.0f / 4.0f, 4.0f / 3.0f, 45.0f / 32.0f,
+                                   3.0f / 2.0f, 8.0f / 5.0f, 5.0f / 3.0f, 9.0f / 5.0f, 15.0f / 8.0f, 2.0f};
+    static const float PYTH[13] = {1.0f, 256.0f / 243.0f, 9.0f / 8.0f, 32.0f / 27.0f, 81.0f / 64.0f, 4.0f / 3.0f,
+                                   729.0f / 512.0f, 3.0f / 2.0f, 128.0f / 81.0f, 27.0f / 16.0f, 32.0f / 9.0f,
+                                   243.0f / 128.0f, 2.0f};
+    static const float ET[13] = {1.0f, 1.0595f, 1.1225f, 1.1892f, 1.2599f, 1.3348f, 1.4142f, 1.4983f, 1.5874f, 1.6818f,
+                                 1.7818f, 1.8877f, 2.0f};
+    if (f_lo == 0.0f) { *accuracy = 0.0f; return 11; }                /* :307-312 */
+    float ratio = f_hi / f_lo;                                        /* :313 */
+    while (ratio > 2.0f) ratio /= 2.0f;                               /* :314-316 */
+    const float *r = system == 1 ? JUST : system == 2 ? PYTH : ET;
+    int idx = 0;
+    float best = fabsf(ratio - r[0]);
+    for (int i = 1; i < 13; ++i) {                                    /* :356-364 min_by: first minimum */
+        const float d = fabsf(ratio - r[i]);
+        if (d < best) { best = d; idx = i; }
+    }
+    *accuracy = -logf(r[idx] / ratio) * 1732.5f;                      /* :381 */
+    return idx == 0 ? 11 : idx - 1;                                   /* :365-379 */
+}
+
+/* Tuner::run's branch for one frame of stable pitches (tuner.rs:148-193).  kind: 0 nothing emitted
+ * (empty list), 1 single note (one pitch, or SinglePitch mode): best = index of the LAST pitch with the
+ * maximum score (Iterator::max_by), 2 interval between the two pitches sorted by frequency, 3 three or
+ * more notes (names only). */
+void aao_tuner_frame(const float *pairs, int n, int system, int single_pitch_mode, int *kind, int *best, int *lo,
+                     int *hi, int *interval, float *accuracy)
+{
+    *kind = 0; *best = 0; *lo = 0; *hi = 0; *interval = 0; *accuracy = 0.0f;
+    if (n <= 0) return;
+    if (n == 1 || single_pitch_mode) {
+        int b = 0;
+        for (int i = 1; i < n; ++i)
+            if (!(pairs[2 * i + 1] < pairs[2 * b + 1])) b = i;     /* total_cmp on finite scores; ties -> last */
+        *kind = 1; *best = b;
+    } else if (n == 2) {
+        const int l = pairs[2] < pairs[0] ? 1 : 0;                   /* sort_by total_cmp, stable */
+        *kind = 2; *lo = l; *hi = 1 - l;
+        *interval = aao_interval(pairs[2 * l], pairs[2 * (1 - l)], system, accuracy);
+    } else {
+        *kind = 3;
+    }
+}

@@ -168,6 +168,10 @@ def lib():
     L.aao_analyze_batch.restype = C.c_int64
     L.aao_analyze_batch.argtypes = [C.POINTER(Config), fp, C.c_int64, C.c_int64, C.c_int, fp, vp, vp]
     L.aao_cond_params_init.argtypes = [C.POINTER(CondParams), C.c_float, C.c_int]
+    L.aao_interval.restype = C.c_int
+    L.aao_interval.argtypes = [C.c_float, C.c_float, C.c_int, fp]
+    ip = C.POINTER(C.c_int)
+    L.aao_tuner_frame.argtypes = [fp, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, fp]
     L.aao_cond_clip.restype = C.c_int64
     L.aao_cond_clip.argtypes = [C.POINTER(CondParams), fp, C.c_int64, vp, C.c_int]
     _lib = L
@@ -377,3 +381,23 @@ def condition_clip(samples: np.ndarray, sample_rate: float, slot_len: int = 1024
     got = lib().aao_cond_clip(C.byref(p), _fp(x), len(x), _vp(dyn), 1 if agc else 0)
     assert got == n_slots
     return x, dyn
+
+
+INT_TYPES = ["Min2", "Maj2", "Min3", "Maj3", "Per4", "Aug4", "Per5", "Min6", "Maj6", "Min7", "Maj7", "Per8"]
+
+
+def interval(f_lo: float, f_hi: float, system: int = 0):
+    """Interval::new (theory.rs:306-382): returns (IntType name, accuracy)."""
+    acc = C.c_float()
+    idx = lib().aao_interval(float(f_lo), float(f_hi), int(system), C.byref(acc))
+    return INT_TYPES[idx], acc.value
+
+
+def tuner_frame(pairs, system: int = 0, single_pitch_mode: bool = False):
+    """Tuner::run's per-frame branch (tuner.rs:148-193) -> dict(kind, best, lo, hi, interval, accuracy)."""
+    a = np.ascontiguousarray(pairs, np.float32).reshape(-1, 2)
+    k, b, lo, hi, iv = (C.c_int() for _ in range(5))
+    acc = C.c_float()
+    lib().aao_tuner_frame(_fp(a), len(a), int(system), 1 if single_pitch_mode else 0, C.byref(k), C.byref(b),
+                          C.byref(lo), C.byref(hi), C.byref(iv), C.byref(acc))
+    return dict(kind=k.value, best=b.value, lo=lo.value, hi=hi.value, interval=iv.value, accuracy=acc.value)

@@ -386,3 +386,41 @@ def test_yin_lag_search_matches_oracle(aa, O, torch_cuda):
     assert abs(int(lag[0, 5]) - round(sr / 110.0)) <= 1 and abs(int(lag[3, 5]) - round(sr / 441.0)) <= 1
     with pytest.raises(aa.AAError):
         aa.yin_host(clips, n, hop, 0, 1024)
+
+
+def test_tuner_records_match_the_reference_branches(aa, O, torch_cuda):
+    """aa_tuner_from_stable_* vs the oracle restatement of Tuner::run / Interval::new (tuner.rs:148-193,
+    theory.rs:306-382; the oracle replays the reference's own Interval tests): kind, indices and interval type
+    are exact; accuracy / cents go through logf / log2f (<= 1 ulp apart): 1e-4 absolute cents."""
+    rng = np.random.default_rng(11)
+    n = 4000
+    st = np.zeros(n, aa.STABLE_DTYPE)
+    st["n"] = rng.integers(0, 5, n)
+    st["n"][:50] = 2
+    f = np.exp(rng.uniform(np.log(50.0), np.log(4000.0), (n, aa.STABLE_DTYPE["pitch"].shape[0]))).astype(np.float32)
+    st["pitch"]["freq"] = f
+    st["pitch"]["score"] = rng.choice([0.25, 0.5, 0.75, 1.0], f.shape).astype(np.float32)     # many score ties
+    st["pitch"]["freq"][:13, 1] = st["pitch"]["freq"][:13, 0] * (np.float32(2.0) ** (np.arange(13, dtype=np.float32) / 12))
+    st["pitch"]["freq"][13, 0] = 0.0
+    for system in (0, 1, 2):
+        for single in (False, True):
+            got = aa.tuner_from_stable(st, 440.0, system, single)
+            for i in range(n):
+                k = int(st["n"][i])
+                pairs = np.stack([st["pitch"]["freq"][i, :k], st["pitch"]["score"][i, :k]], axis=1) if k else np.zeros((0, 2))
+                r = O.tuner_frame(pairs, system, single)
+                g = got[i]
+                assert (g["kind"], g["best"], g["lo"], g["hi"]) == (r["kind"], r["best"], r["lo"], r["hi"]), (i, system, single)
+                if r["kind"] == 2:
+                    near_tie = False
+                    if g["interval"] != r["interval"]:      # |ratio - r_i| == |ratio - r_j| to the last ulp: not expected
+                        near_tie = True
+                    assert not near_tie
+                    assert abs(g["accuracy"] - r["accuracy"]) <= 1e-4 * max(1.0, abs(r["accuracy"]))
+                    assert g["cents"] == g["accuracy"]
+                if r["kind"] == 1:
+                    cents = O.note_from_freq(float(st["pitch"]["freq"][i, r["best"]]), 440.0)[3]
+                    assert abs(g["cents"] - cents) <= 2e-3
+    assert aa.INT_TYPES[aa.tuner_from_stable(st[:13], 440.0, 0, False)["interval"][7]] == "Per5"
+    with pytest.raises(aa.AAError):
+        aa.tuner_from_stable(st, 440.0, 3, False)

@@ -228,3 +228,30 @@ def test_only_full_slots_are_processed(O):
     assert len(dyn) == 3
     assert np.array_equal(y[3 * L:], x[3 * L:])         # mod.rs:799-803: a partial slot is never delivered
     assert not np.array_equal(y[:3 * L], x[:3 * L])
+
+
+# ---- tuner post-stage: PINNED by the reference's own known-answer tests -------------
+
+def test_interval_known_answers_of_the_reference(O):
+    """theory.rs:545-583: the reference's own Interval tests, replayed on the oracle."""
+    c4 = np.float32(261.63)
+    for semis, name in [(7, "Per5"), (12, "Per8"), (4, "Maj3"), (3, "Min3"), (5, "Per4")]:
+        hi = c4 * np.float32(2.0) if semis == 12 else c4 * np.float32(2.0) ** np.float32(semis / 12.0)
+        got, acc = O.interval(float(c4), float(hi), 0)
+        assert got == name and abs(acc) < 1.0
+    # theory.rs:307-312: a zero first frequency returns the Per8 default instead of dividing by zero
+    assert O.interval(0.0, 440.0, 0) == ("Per8", 0.0)
+    # ratios above an octave fold down (:314-316); the three tuning systems use their own tables
+    assert O.interval(220.0, 660.0, 0)[0] == "Per5" and O.interval(220.0, 660.0, 1) == ("Per5", pytest.approx(0.0, abs=1e-3))
+    assert O.interval(243.0, 256.0, 2)[0] == "Min2" and abs(O.interval(243.0, 256.0, 2)[1]) < 1e-3
+
+
+def test_tuner_frame_branches(O):
+    """tuner.rs:152-193."""
+    assert O.tuner_frame(np.zeros((0, 2)))["kind"] == 0
+    assert O.tuner_frame([[440.0, 0.4]]) == dict(kind=1, best=0, lo=0, hi=0, interval=0, accuracy=0.0)
+    r = O.tuner_frame([[660.0, 0.4], [440.0, 0.9]])
+    assert (r["kind"], r["lo"], r["hi"], O.INT_TYPES[r["interval"]]) == (2, 1, 0, "Per5")
+    assert O.tuner_frame([[440.0, 0.4], [550.0, 0.9], [660.0, 0.9]])["kind"] == 3
+    # SinglePitch mode: the highest score wins, the LAST one on ties (Iterator::max_by)
+    assert O.tuner_frame([[440.0, 0.4], [550.0, 0.9], [660.0, 0.9]], 0, True)["best"] == 2
