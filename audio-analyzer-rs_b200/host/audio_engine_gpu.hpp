@@ -10,6 +10,10 @@
 //   OnsetDetector         src/analysis/onset.rs:21-546  new / detect_onsets / stop / pause / resume
 //   PitchFrame            the (Vec<(f32,f32)>, f64) pushed on note_tx (stft.rs:431-434)
 //   OnsetEvent            src/audio_io/timing.rs:77-87
+//   Reducer               the reducer thread's per-slot work, src/audio_io/mod.rs:431-490
+//                         (HPF / LPF / gate + DynamicsTracker::process_slot, dynamics.rs:194-360)
+//   DynamicsOutput        src/audio_io/dynamics.rs:78-104
+//   Tuner / TunerOutput   src/analysis/tuner.rs:27-208 (per-frame branch; labels formatted here)
 //
 // What stays on the host, exactly as in the reference: the worker thread and its
 // stop/pause/resume state machine (AtomicI8 -1/0/1, stft.rs:127-135), the slot
@@ -349,6 +353,125 @@ public:
 private:
     aa_config cfg_;
     aa_analyzer *h_ = nullptr;
+};
+
+// ---------------------------------------------------------------------------
+// Reducer: what the reducer thread does to every slot before it fans the slot out to the analyzers
+// (src/audio_io/mod.rs:431-490).  The filters, the gate and DynamicsTracker::process_slot run behind
+// aa_condition_host with the state carried in the handle; the consumer bookkeeping stays on the host.
+// ---------------------------------------------------------------------------
+enum class DynamicLevel { Silence, Ppp, Pp, P, Mp, Mf, F, Ff, Fff };     // dynamics.rs:49-60
+inline const char *to_string(DynamicLevel l)                             // dynamics.rs:62-77
+{
+    static const char *n[] = {"silence", "ppp", "pp", "p", "mp", "mf", "f", "ff", "fff"};
+    return n[static_cast<int>(l)];
+}
+struct DynamicsOutput {                                                  // dynamics.rs:78-104
+    DynamicLevel level = DynamicLevel::Silence;
+    float rms_db = -96.0f, gain_db = 0.0f, session_median_db = -96.0f, noise_floor_db = -96.0f;
+};
+
+class Reducer {
+public:
+    // sample_rate / slot_len as in AudioPipeline (mod.rs:330-355); AGC target -18 dBFS, 240 s smoothing
+    Reducer(float sample_rate, int32_t slot_len = 1024)
+    {
+        cfg_.sample_rate = sample_rate;
+        cfg_.slot_len = slot_len;
+        cfg_.flags = AA_COND_AGC | AA_COND_CARRY;
+        check(aa_conditioner_create(&cfg_, &h_));
+    }
+    ~Reducer() { aa_conditioner_destroy(h_); }
+    Reducer(const Reducer &) = delete;
+    Reducer &operator=(const Reducer &) = delete;
+    // one slot, in place (mod.rs:433-490); the returned value is what the reference publishes into
+    // Arc<RwLock<DynamicsOutput>> (dynamics.rs:355-362)
+    DynamicsOutput process_slot(float *slot, size_t len)
+    {
+        if (len != static_cast<size_t>(cfg_.slot_len)) throw Error(AA_ERR_INVALID, "Reducer::process_slot: wrong slot length");
+        aa_dynamics d{};
+        check(aa_condition_host(h_, slot, 1, cfg_.slot_len, cfg_.slot_len, &d));
+        DynamicsOutput o;
+        o.level = static_cast<DynamicLevel>(d.level);
+        o.rms_db = d.rms_db;
+        o.gain_db = d.gain_db;
+        o.session_median_db = d.session_median_db;
+        o.noise_floor_db = d.noise_floor_db;
+        return o;
+    }
+    void reset() { check(aa_conditioner_reset(h_)); }
+
+private:
+    aa_cond_config cfg_{};
+    aa_conditioner *h_ = nullptr;
+};
+
+// ---------------------------------------------------------------------------
+// Tuner (src/analysis/tuner.rs): the per-frame branch of Tuner::run with Note::from_freq and
+// Interval::new evaluated on the device (aa_notes_from_stable_host, aa_tuner_from_stable_host); the
+// label strings of TunerOutput (tuner.rs:27-52) are formatted here from the numeric records.
+// ---------------------------------------------------------------------------
+enum class TuningSystem { EqualTemperament = 0, JustIntonation = 1, Pythagorean = 2 };   // tuner.rs:13-18
+enum class TunerMode { MultiPitch = 0, SinglePitch = 1 };                                // tuner.rs:21-25
+struct TunerOutput {
+    std::string label;
+    float cents = 0.0f;
+    std::vector<std::string> notes;
+    std::vector<float> accuracies;
+};
+
+class Tuner {
+public:
+    TuningSystem system = TuningSystem::EqualTemperament;
+    TunerMode mode = TunerMode::MultiPitch;
+    float base = 440.0f;
+
+    static std::string note_name(const aa_note &n)                                       // theory.rs:234-246
+    {
+        static const char *names[] = {"C", "C#", "D", "D#", "E", "F", "F#", "G", "G#", "A", "A#", "B"};
+        return std::string(names[n.semis % 12]) + std::to_string(static_cast<int>(n.octave));
+    }
+    static const char *interval_name(uint32_t t)                                         // theory.rs:285-298, 384-386
+    {
+        static const char *names[] = {"Min2", "Maj2", "Min3", "Maj3", "Per4", "Aug4", "Per5", "Min6", "Maj6", "Min7",
+                                      "Maj7", "Per8"};
+        return names[t < 12 ? t : 11];
+    }
+    // One batch of frames (as popped from note_rx, tuner.rs:141-150); empty frames give an empty label.
+    std::vector<TunerOutput> run(const aa_stable_pitches *frames, int64_t n_frames) const
+    {
+        std::vector<aa_note_record> notes(static_cast<size_t>(n_frames));
+        std::vector<aa_tuner_record> rec(static_cast<size_t>(n_frames));
+        std::vector<TunerOutput> out(static_cast<size_t>(n_frames));
+        if (n_frames == 0) return out;
+        check(aa_notes_from_stable_host(frames, n_frames, base, notes.data()));
+        check(aa_tuner_from_stable_host(frames, n_frames, base, static_cast<int32_t>(system),
+                                        mode == TunerMode::SinglePitch ? 1 : 0, rec.data()));
+        for (int64_t f = 0; f < n_frames; ++f) {
+            const aa_tuner_record &r = rec[static_cast<size_t>(f)];
+            const aa_note_record &nr = notes[static_cast<size_t>(f)];
+            TunerOutput &o = out[static_cast<size_t>(f)];
+            o.cents = r.cents;
+            if (r.kind == 1) {                                                           // tuner.rs:158-166
+                o.label = note_name(nr.note[r.best]);
+                o.notes.push_back(o.label);
+                o.accuracies.push_back(nr.note[r.best].cents);
+            } else if (r.kind == 2) {                                                    // tuner.rs:167-181
+                for (uint8_t i : {r.lo, r.hi}) {
+                    o.notes.push_back(note_name(nr.note[i]));
+                    o.accuracies.push_back(nr.note[i].cents);
+                }
+                o.label = interval_name(r.interval);
+            } else if (r.kind == 3) {                                                    // tuner.rs:182-189
+                for (uint32_t i = 0; i < nr.n && i < AA_MAX_STABLE; ++i) {
+                    o.notes.push_back(note_name(nr.note[i]));
+                    o.accuracies.push_back(nr.note[i].cents);
+                    o.label += (i ? " " : "") + o.notes.back();
+                }
+            }
+        }
+        return out;
+    }
 };
 
 }  // namespace audio_engine_gpu

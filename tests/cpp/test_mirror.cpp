@@ -108,5 +108,44 @@ int main(int argc, char **argv)
         if (!shared.onset_pending.load()) return fail("onset_pending not set");
         std::printf("ok: OnsetDetector emitted %zu events, velocity %.2f\n", ev.size(), ev[0].velocity);
     }
+    // ---- Reducer: a -20 dBFS 440 Hz tone slot by slot -> "mf", DC removed, gain creeping up ----
+    {
+        const float sr = 48000.0f;
+        Reducer red(sr, 1024);
+        DynamicsOutput last;
+        float peak = 0.0f;
+        for (int s = 0; s < 60; ++s) {
+            std::vector<float> slot(1024);
+            for (int i = 0; i < 1024; ++i)
+                slot[i] = 0.05f + (float)(0.1414 * std::sin(2.0 * M_PI * 440.0 * (double)(s * 1024 + i) / sr));
+            last = red.process_slot(slot.data(), slot.size());
+            if (s == 59) for (float v : slot) peak = std::fmax(peak, std::fabs(v));
+        }
+        if (last.level != DynamicLevel::Mf || std::fabs(last.rms_db + 20.0f) > 0.1f || !(last.gain_db > 0.0f))
+            return fail("Reducer dynamics");
+        if (std::fabs(peak - 0.1414f) > 0.004f) return fail("Reducer did not remove the DC offset");
+        bool threw = false;
+        std::vector<float> bad(1000);
+        try { red.process_slot(bad.data(), bad.size()); } catch (const Error &) { threw = true; }
+        if (!threw) return fail("Reducer accepted a wrong slot length");
+        std::printf("ok: Reducer level %s rms %.2f dB gain %.4f dB\n", to_string(last.level), last.rms_db, last.gain_db);
+    }
+    // ---- Tuner: single note, a perfect fifth, a triad ----
+    {
+        std::vector<aa_stable_pitches> fr(4);
+        std::memset(fr.data(), 0, sizeof(aa_stable_pitches) * fr.size());
+        fr[1].n = 1; fr[1].pitch[0] = {440.0f, 0.6f};
+        fr[2].n = 2; fr[2].pitch[0] = {392.0f, 0.5f}; fr[2].pitch[1] = {261.63f, 0.7f};
+        fr[3].n = 3; fr[3].pitch[0] = {261.63f, 0.5f}; fr[3].pitch[1] = {329.63f, 0.5f}; fr[3].pitch[2] = {392.0f, 0.5f};
+        Tuner tuner;
+        const std::vector<TunerOutput> out = tuner.run(fr.data(), (int64_t)fr.size());
+        if (!out[0].label.empty()) return fail("Tuner: empty frame");
+        if (out[1].label != "A4" || std::fabs(out[1].cents) > 2.0f) return fail("Tuner: A4");
+        if (out[2].label != "Per5" || out[2].notes.size() != 2 || out[2].notes[0] != "C4" || out[2].notes[1] != "G4")
+            return fail("Tuner: fifth");
+        if (out[3].label != "C4 E4 G4") return fail("Tuner: triad");
+        std::printf("ok: Tuner labels %s / %s (%.2f cents) / %s\n", out[1].label.c_str(), out[2].label.c_str(), out[2].cents,
+                    out[3].label.c_str());
+    }
     return 0;
 }

@@ -33,3 +33,4 @@ def test_cpp_mirror_on_gpu(aa, torch_cuda, tmp_path):
     out = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "STFT emitted 76 frames" in out.stdout and "OnsetDetector emitted" in out.stdout
+    assert "Reducer level mf" in out.stdout and "Tuner labels A4 / Per5" in out.stdout
