@@ -634,8 +634,10 @@ struct aa_stream {
     aa_stable_pitches *d_stab = nullptr;
     uint8_t *d_onset = nullptr;
     uint8_t *h_onset = nullptr;          // pinned
-    aa_frame_features *h_feat = nullptr; // pinned ring
-    aa_stable_pitches *h_stab = nullptr; // pinned ring
+    aa_frame_features *h_feat = nullptr; // pinned ring (mapped)
+    aa_stable_pitches *h_stab = nullptr; // pinned ring (mapped)
+    aa_frame_features *m_feat = nullptr; // device addresses of the mapped rings
+    aa_stable_pitches *m_stab = nullptr;
     int64_t max_frames_per_push = 0;
     int64_t out_cap = 0;                 // frames in the host result ring
     int64_t out_head = 0, out_count = 0; // ring of completed frames
@@ -686,8 +688,12 @@ extern "C" AA_API aa_status aa_stream_create(const aa_config *cfg, aa_stream **o
     ok(cudaMalloc(&h->d_onset, h->max_frames_per_push));
     ok(cudaHostAlloc(&h->h_stage, sizeof(float) * ring, cudaHostAllocDefault));
     ok(cudaHostAlloc(&h->h_onset, h->max_frames_per_push, cudaHostAllocDefault));
-    ok(cudaHostAlloc(&h->h_feat, sizeof(aa_frame_features) * h->out_cap, cudaHostAllocDefault));
-    ok(cudaHostAlloc(&h->h_stab, sizeof(aa_stable_pitches) * h->out_cap, cudaHostAllocDefault));
+    // the result ring is mapped into the device address space: the kernel writes the records of a push
+    // straight into it (no device-to-host copies on the latency path) whenever they do not wrap around
+    ok(cudaHostAlloc(&h->h_feat, sizeof(aa_frame_features) * h->out_cap, cudaHostAllocMapped));
+    ok(cudaHostAlloc(&h->h_stab, sizeof(aa_stable_pitches) * h->out_cap, cudaHostAllocMapped));
+    ok(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->m_feat), h->h_feat, 0));
+    ok(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->m_stab), h->h_stab, 0));
     if (e == cudaSuccess) ok(cudaMemsetAsync(h->d_state, 0, sizeof(float) * state_floats(h->half), h->s));
     if (e == cudaSuccess) ok(cudaStreamSynchronize(h->s));
     if (e != cudaSuccess) {
@@ -762,29 +768,33 @@ extern "C" AA_API aa_status aa_stream_push(aa_stream *h, const float *samples, i
         return fail(AA_ERR_OVERFLOW, "aa_stream_push: result ring full, call aa_stream_poll");
     if (h->rd & 3) return fail(AA_ERR_INVALID, "aa_stream: hop must keep the read position 16-byte aligned");
 
-    const bool use_onset = (h->an->cfg.features & AA_FEAT_TRACKER) != 0;
+    // onset_pending (stft.rs:387) reaches the tracker as a per-frame flag array; without a pending onset the
+    // kernel takes a null array as "no onsets" and the copy is skipped
+    const bool use_onset = (h->an->cfg.features & AA_FEAT_TRACKER) != 0 && h->onset_pending;
     if (use_onset) {
         std::memset(h->h_onset, 0, (size_t)T);
-        if (h->onset_pending) h->h_onset[0] = 1;
+        h->h_onset[0] = 1;
         h->onset_pending = false;
         CU(cudaMemcpyAsync(h->d_onset, h->h_onset, (size_t)T, cudaMemcpyHostToDevice, h->s));
     }
+    // results: straight into the mapped host ring when the T records are contiguous there, else through the
+    // device buffers and two-segment copies
+    const int64_t tail = (h->out_head + h->out_count) % h->out_cap;
+    const int64_t first = std::min(T, h->out_cap - tail);
+    const bool direct = first == T;
     aa_outputs od{};
-    od.features = h->d_feat;
-    od.stable = h->d_stab;
+    od.features = direct ? h->m_feat + tail : h->d_feat;
+    od.stable = direct ? h->m_stab + tail : h->d_stab;
     const int64_t clip_len = h->n + (T - 1) * h->hop;
     int64_t launches = 0;
     aa_status st = analyze_device_impl(h->an, h->d_buf[h->cur] + h->rd, 1, clip_len, (clip_len + 3) & ~(int64_t)3,
                                        use_onset ? h->d_onset : nullptr, &od, h->d_state, h->s, &launches);
     if (st != AA_OK) return st;
-    // results into the host ring (two segments if it wraps)
-    int64_t tail = (h->out_head + h->out_count) % h->out_cap;
-    int64_t first = std::min(T, h->out_cap - tail);
-    CU(cudaMemcpyAsync(h->h_feat + tail, h->d_feat, sizeof(aa_frame_features) * (size_t)first,
-                       cudaMemcpyDeviceToHost, h->s));
-    CU(cudaMemcpyAsync(h->h_stab + tail, h->d_stab, sizeof(aa_stable_pitches) * (size_t)first,
-                       cudaMemcpyDeviceToHost, h->s));
-    if (first < T) {
+    if (!direct) {
+        CU(cudaMemcpyAsync(h->h_feat + tail, h->d_feat, sizeof(aa_frame_features) * (size_t)first,
+                           cudaMemcpyDeviceToHost, h->s));
+        CU(cudaMemcpyAsync(h->h_stab + tail, h->d_stab, sizeof(aa_stable_pitches) * (size_t)first,
+                           cudaMemcpyDeviceToHost, h->s));
         CU(cudaMemcpyAsync(h->h_feat, h->d_feat + first, sizeof(aa_frame_features) * (size_t)(T - first),
                            cudaMemcpyDeviceToHost, h->s));
         CU(cudaMemcpyAsync(h->h_stab, h->d_stab + first, sizeof(aa_stable_pitches) * (size_t)(T - first),
