@@ -29,6 +29,10 @@ from ._ffi import (  # noqa: F401
     FLAG_FLUX_ONSET,
     FLAG_ONSET_FIRED,
     NOTE_NAMES,
+    PCM_F32,
+    PCM_I16,
+    PCM_U16,
+    ingest_device,
     NOTE_RECORD_DTYPE,
     FLAG_ONSET_DETECTED,
     FftProcessor,

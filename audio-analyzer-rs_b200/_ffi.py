@@ -90,6 +90,8 @@ class Config(C.Structure):
 
 
 COND_AGC, COND_CARRY = 1, 2
+PCM_F32, PCM_I16, PCM_U16 = 0, 1, 2
+PCM_DTYPES = {0: np.float32, 1: np.int16, 2: np.uint16}
 
 
 class CondConfig(C.Structure):
@@ -182,6 +184,8 @@ def lib():
         "aa_yin_host": (i32, [vp, vp, i64, i64, i64, vp, vp]),
         "aa_notes_from_stable_device": (i32, [vp, i64, f32, vp, vp]),
         "aa_notes_from_stable_host": (i32, [vp, i64, f32, vp]),
+        "aa_ingest_device": (i32, [vp, i32, i32, i64, i64, i64, i64, vp, vp]),
+        "aa_analyze_host_pcm": (i32, [vp, vp, i32, i32, i64, i64, i64, vp, C.POINTER(_Outputs)]),
         "aa_tuner_from_stable_device": (i32, [vp, i64, f32, i32, i32, vp, vp]),
         "aa_tuner_from_stable_host": (i32, [vp, i64, f32, i32, i32, vp]),
         "aa_conditioner_create": (i32, [C.POINTER(CondConfig), pvp]),
@@ -343,6 +347,33 @@ class Analyzer:
                      _ptr(dbg_peaks))
         _check(lib().aa_analyze_host(self._h, _ptr(clips), n_clips, clip_len, clip_stride, _ptr(onset_in),
                                      C.byref(o)))
+
+    def analyze_host_pcm(self, pcm: np.ndarray, fmt: int, channels: int, want_mags=True, want_stable=True,
+                         want_summaries=True):
+        """aa_analyze_host_pcm: pcm [n_clips, clip_len * channels] interleaved (float32 / int16 / uint16 per fmt);
+        clip_len (frames) must be a multiple of 4 here because the rows are contiguous."""
+        pcm = np.ascontiguousarray(pcm, PCM_DTYPES.get(fmt, np.int16))     # an unknown format is rejected by the ABI
+        n_clips, row = pcm.shape
+        clen = row // channels
+        if row % channels or clen % 4:
+            raise AAError(-1, "row length must be channels * clip_len with clip_len % 4 == 0")
+        T = self.num_frames(clen)
+        res = {"T": T}
+        res["features"] = np.zeros((n_clips, T), FEATURES_DTYPE)
+        res["mags"] = np.zeros((n_clips, T, self.half), np.float32) if want_mags else None
+        res["stable"] = np.zeros((n_clips, T), STABLE_DTYPE) if want_stable else None
+        res["summaries"] = np.zeros(n_clips, SUMMARY_DTYPE) if want_summaries else None
+        o = _Outputs(_ptr(res["mags"]), _ptr(res["features"]), _ptr(res["stable"]), _ptr(res["summaries"]), None, None)
+        _check(lib().aa_analyze_host_pcm(self._h, _ptr(pcm), int(fmt), int(channels), n_clips, clen, clen, None,
+                                         C.byref(o)))
+        return res
+
+    def analyze_host_pcm_into(self, pcm: np.ndarray, fmt: int, channels: int, n_clips: int, clip_len: int,
+                              clip_stride: int, features=None, stable=None, summaries=None):
+        """aa_analyze_host_pcm on caller-provided (ideally pinned) arrays."""
+        o = _Outputs(None, _ptr(features), _ptr(stable), _ptr(summaries), None, None)
+        _check(lib().aa_analyze_host_pcm(self._h, _ptr(pcm), int(fmt), int(channels), n_clips, clip_len, clip_stride,
+                                         None, C.byref(o)))
 
     def analyze_host(self, clips: np.ndarray, want_mags=True, want_stable=True, want_summaries=True,
                      want_dbg=False, onset_in=None, clip_stride=None, clip_len=None):
@@ -517,3 +548,10 @@ def tuner_from_stable(stable: np.ndarray, base_freq: float = 440.0, system: int 
     _check(lib().aa_tuner_from_stable_host(_ptr(st), st.shape[0], float(base_freq), int(system),
                                            1 if single_pitch_mode else 0, _ptr(out)))
     return out.reshape(np.shape(stable))
+
+
+def ingest_device(pcm_ptr: int, fmt: int, channels: int, n_clips: int, clip_len: int, in_stride: int, out_stride: int,
+                  out_ptr: int, stream: int = 0):
+    """aa_ingest_device: interleaved PCM (f32 / i16 / u16) -> mono f32 clips (mod.rs:765-792)."""
+    _check(lib().aa_ingest_device(C.c_void_p(pcm_ptr), int(fmt), int(channels), n_clips, clip_len, in_stride, out_stride,
+                                  C.c_void_p(out_ptr), C.c_void_p(stream) if stream else None))

@@ -362,6 +362,8 @@ static void fill_params(const aa_config &cfg, const Tables &tab, AnalyzeParams *
 struct StageSlot {
     float *in = nullptr;
     size_t in_cap = 0;
+    uint8_t *raw = nullptr;      // interleaved PCM as it came from the host (aa_analyze_host_pcm)
+    size_t raw_cap = 0;
     float *mags = nullptr;
     size_t mags_cap = 0;
     aa_frame_features *feat = nullptr;
@@ -425,7 +427,7 @@ extern "C" AA_API aa_status aa_analyzer_create(const aa_config *cfg, aa_analyzer
 
 static void free_slot(StageSlot &s)
 {
-    cudaFree(s.in); cudaFree(s.mags); cudaFree(s.feat); cudaFree(s.stable); cudaFree(s.summ);
+    cudaFree(s.in); cudaFree(s.raw); cudaFree(s.mags); cudaFree(s.feat); cudaFree(s.stable); cudaFree(s.summ);
     cudaFree(s.onset); cudaFree(s.dbg_floor); cudaFree(s.dbg_peaks);
     if (s.h2d_done) cudaEventDestroy(s.h2d_done);
     if (s.k_done) cudaEventDestroy(s.k_done);
@@ -521,12 +523,16 @@ static aa_status grow(Tp **p, size_t *cap, size_t need)
     return AA_OK;
 }
 
-extern "C" AA_API aa_status aa_analyze_host(aa_analyzer *h, const float *clips_host, int64_t n_clips,
-                                            int64_t clip_len, int64_t clip_stride,
-                                            const uint8_t *onset_in_host, const aa_outputs *out_host)
+// format / channels: what the host buffer holds (AA_PCM_*, interleaved); mono f32 is copied straight into the
+// analysis input, anything else goes through the ingest kernel (mod.rs:765-792) on the device
+static aa_status analyze_host_impl(aa_analyzer *h, const void *clips_host, int format, int channels, int64_t n_clips,
+                                   int64_t clip_len, int64_t clip_stride, const uint8_t *onset_in_host,
+                                   const aa_outputs *out_host)
 {
     if (!h || !clips_host || !out_host || n_clips < 0 || clip_len < 0 || clip_stride < 0)
         return fail(AA_ERR_INVALID, "aa_analyze_host: bad argument");
+    const bool direct = format == AA_PCM_F32 && channels == 1;
+    const size_t sample_bytes = format == AA_PCM_F32 ? 4 : 2;
     CU(cudaSetDevice(h->device));
     h->launches = 0;
     const int64_t T = aa_num_frames(&h->cfg, clip_len);
@@ -565,14 +571,26 @@ extern "C" AA_API aa_status aa_analyze_host(aa_analyzer *h, const float *clips_h
         if (onset_in_host && (st = grow(&sl.onset, &sl.onset_cap, frames)) != AA_OK) return st;
 
         // H2D (the kernel that last read this slot's input has finished: d2h_done above implies k_done)
-        CU(cudaMemcpyAsync(sl.in, clips_host + c0 * clip_stride, span * sizeof(float), cudaMemcpyHostToDevice,
-                           h->s_h2d));
+        if (direct) {
+            CU(cudaMemcpyAsync(sl.in, static_cast<const float *>(clips_host) + c0 * clip_stride, span * sizeof(float),
+                               cudaMemcpyHostToDevice, h->s_h2d));
+        } else {
+            const size_t frame_bytes = sample_bytes * (size_t)channels;
+            if ((st = grow(&sl.raw, &sl.raw_cap, span * frame_bytes + 16)) != AA_OK) return st;
+            CU(cudaMemcpyAsync(sl.raw, static_cast<const uint8_t *>(clips_host) + (size_t)(c0 * clip_stride) * frame_bytes,
+                               span * frame_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+        }
         if (onset_in_host)
             CU(cudaMemcpyAsync(sl.onset, onset_in_host + c0 * T, frames, cudaMemcpyHostToDevice, h->s_h2d));
         CU(cudaEventRecord(sl.h2d_done, h->s_h2d));
 
         // kernels
         CU(cudaStreamWaitEvent(h->s_compute, sl.h2d_done, 0));
+        if (!direct) {
+            CU(launch_ingest(sl.raw, format, channels, nc, clip_len, clip_stride, clip_stride, sl.in, h->num_sms,
+                             h->s_compute));
+            ++h->launches;
+        }
         aa_outputs od{};
         od.mags = out_host->mags ? sl.mags : nullptr;
         od.features = out_host->features || out_host->summaries ? sl.feat : nullptr;
@@ -612,6 +630,47 @@ extern "C" AA_API aa_status aa_analyze_host(aa_analyzer *h, const float *clips_h
     }
     CU(cudaStreamSynchronize(h->s_d2h));
     CU(cudaStreamSynchronize(h->s_compute));
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_analyze_host(aa_analyzer *h, const float *clips_host, int64_t n_clips,
+                                            int64_t clip_len, int64_t clip_stride,
+                                            const uint8_t *onset_in_host, const aa_outputs *out_host)
+{
+    return analyze_host_impl(h, clips_host, AA_PCM_F32, 1, n_clips, clip_len, clip_stride, onset_in_host, out_host);
+}
+
+static aa_status pcm_check(int32_t format, int32_t channels, const char *who)
+{
+    if (format != AA_PCM_F32 && format != AA_PCM_I16 && format != AA_PCM_U16)
+        return fail(AA_ERR_INVALID, std::string(who) + ": format must be AA_PCM_F32, AA_PCM_I16 or AA_PCM_U16");
+    if (channels < 1 || channels > 64) return fail(AA_ERR_INVALID, std::string(who) + ": 1 <= channels <= 64");
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_analyze_host_pcm(aa_analyzer *h, const void *pcm_host, int32_t format, int32_t channels,
+                                                int64_t n_clips, int64_t clip_len, int64_t clip_stride,
+                                                const uint8_t *onset_in_host, const aa_outputs *out_host)
+{
+    aa_status st = pcm_check(format, channels, "aa_analyze_host_pcm");
+    if (st != AA_OK) return st;
+    return analyze_host_impl(h, pcm_host, format, channels, n_clips, clip_len, clip_stride, onset_in_host, out_host);
+}
+
+extern "C" AA_API aa_status aa_ingest_device(const void *pcm_dev, int32_t format, int32_t channels, int64_t n_clips,
+                                             int64_t clip_len, int64_t in_stride, int64_t out_stride, float *mono_dev,
+                                             void *stream)
+{
+    aa_status st = pcm_check(format, channels, "aa_ingest_device");
+    if (st != AA_OK) return st;
+    if (!pcm_dev || !mono_dev || n_clips < 0 || clip_len < 0 || in_stride < 0 || out_stride < 0 ||
+        (reinterpret_cast<uintptr_t>(pcm_dev) & 15) || (reinterpret_cast<uintptr_t>(mono_dev) & 15))
+        return fail(AA_ERR_INVALID, "aa_ingest_device: null, negative or not 16-byte aligned argument");
+    int sms = 0;
+    st = check_device(&sms);
+    if (st != AA_OK) return st;
+    CU(launch_ingest(pcm_dev, format, channels, n_clips, clip_len, in_stride, out_stride, mono_dev, sms,
+                     (cudaStream_t)stream));
     return AA_OK;
 }
 

@@ -291,12 +291,34 @@ def run_ours(a):
         e2e = {"seconds": e2e_s, "launches": e2e_launches, "matches_device_path": same,
                "h2d": int(h_clips.nbytes),
                "d2h": int(h_feat.nbytes + (h_stab.nbytes if h_stab is not None else 0) + h_summ.nbytes)}
+        # The same call on 16-bit mono PCM (the reference's input callback takes i16 devices too, mod.rs:691):
+        # the samples are the batch quantised to i16, converted on the device (aa_analyze_host_pcm), so the
+        # PCIe-bound path moves half the bytes.  Reported beside e2e, not instead of it.
+        h_pcm = aa.pinned_empty((n_clips, clip_len), np.int16)
+        np.multiply(h_clips, 32767.0, out=h_clips)
+        np.rint(h_clips, out=h_clips)
+        h_pcm[...] = h_clips
+        del h_clips
+
+        def pcm_step():
+            an.analyze_host_pcm_into(h_pcm, aa.PCM_I16, 1, n_clips, clip_len, clip_len, features=h_feat,
+                                     stable=h_stab, summaries=h_summ)
+
+        pcm_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            pcm_step()
+        torch.cuda.synchronize()
+        e2e["pcm16_seconds"] = time.perf_counter() - t0
+        e2e["pcm16_h2d"] = int(h_pcm.nbytes)
 
     # ---- reduce over ranks (max time) -----------------------------------------------------------
-    times = torch.tensor([ms, kernel_ms, e2e["seconds"] if e2e else 0.0], device=dev, dtype=torch.float64)
+    times = torch.tensor([ms, kernel_ms, e2e["seconds"] if e2e else 0.0, e2e["pcm16_seconds"] if e2e else 0.0],
+                         device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, kernel_ms, e2e_s = (float(v) for v in times.tolist())
+    ms, kernel_ms, e2e_s, pcm_s = (float(v) for v in times.tolist())
 
     if rank == 0:
         total_frames = world * frames * a.steps
@@ -329,6 +351,11 @@ def run_ours(a):
                 "ms_per_step": 1e3 * e2e_s / a.steps, "launches": e2e["launches"],
                 "matches_device_path": e2e["matches_device_path"],
                 "outputs": "feature records + stable pitches + summaries (magnitudes stay on device)",
+            }
+            line["e2e_pcm16"] = {
+                "value": world * frames * a.steps / pcm_s, "unit": "frames/s", "h2d_bytes_per_step": e2e["pcm16_h2d"],
+                "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": 1e3 * pcm_s / a.steps,
+                "input": "the same batch as 16-bit mono PCM, converted on the device (aa_analyze_host_pcm)",
             }
         if world == 1 and not a.no_cpu:
             threads = os.cpu_count() or 1

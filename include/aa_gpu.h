@@ -183,6 +183,22 @@ AA_API aa_status aa_analyze_host(aa_analyzer *h, const float *clips_host, int64_
 /* Number of kernel launches issued by the last aa_analyze_* call on this handle. */
 AA_API int64_t   aa_analyzer_last_launches(const aa_analyzer *h);
 
+/* Device sample formats.  The reference's input callback (src/audio_io/mod.rs:657-716, 765-792) accepts f32, i16
+ * and u16 devices with any channel count, converts every sample with cpal / dasp_sample's `to_sample::<f32>()`
+ * (i16: s / 32768, u16: (s - 32768) / 32768) and mixes the first min(channels, 2) channels of a frame:
+ * mixed = (0.0 + s0 [+ s1]) / channels_to_use.  aa_ingest_device does exactly that on the device;
+ * aa_analyze_host_pcm is aa_analyze_host on interleaved PCM (clip_len / clip_stride count frames): 16-bit mono
+ * input halves the host-to-device bytes of the end-to-end path, which is PCIe-bound. */
+#define AA_PCM_F32 0
+#define AA_PCM_I16 1
+#define AA_PCM_U16 2
+AA_API aa_status aa_ingest_device(const void *pcm_dev, int32_t format, int32_t channels, int64_t n_clips,
+                                  int64_t clip_len, int64_t in_stride, int64_t out_stride, float *mono_dev,
+                                  void *stream);
+AA_API aa_status aa_analyze_host_pcm(aa_analyzer *h, const void *pcm_host, int32_t format, int32_t channels,
+                                     int64_t n_clips, int64_t clip_len, int64_t clip_stride,
+                                     const uint8_t *onset_in_host, const aa_outputs *out_host);
+
 /* ------------------------------------------------------------------------- *
  * Note identification of the tuner stage (NEXT row f2): Note::from_freq
  * (src/analysis/theory.rs:195-209) applied to every stable pitch, as numbers

@@ -219,6 +219,7 @@ void      aao_cond_agc(aao_cond *c, float *slot, int len, aao_dynamics *out, int
 int       aao_interval(float f_lo, float f_hi, int system, float *accuracy);
 void      aao_tuner_frame(const float *pairs, int n, int system, int single_pitch_mode, int *kind, int *best, int *lo,
                           int *hi, int *interval, float *accuracy);
+void      aao_ingest(const void *pcm, int format, int channels, int64_t n_frames, float *out);
 int64_t   aao_cond_clip(const aao_cond_params *p, float *samples, int64_t len, aao_dynamics *dyn, int agc);
 
 #ifdef __cplusplus

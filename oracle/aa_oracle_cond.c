@@ -314,3 +314,27 @@ void aao_tuner_frame(const float *pairs, int n, int system, int single_pitch_mod
         *kind = 3;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Input callback: device sample format -> mono f32 slot (src/audio_io/mod.rs:765-792).
+ *   channels_to_use = min(channels, 2);  mixed = fold(0.0f32, acc + s.to_sample::<f32>()) / channels_to_use
+ * `to_sample` is cpal 0.16.0's re-export of dasp_sample 0.11.0 (Cargo.lock:1768-1770, 2003-2005; crate not
+ * vendored): i16 -> f32 is `s as f32 / 32_768.0`, u16 -> f32 goes through i16 (`s - 32768`), f32 is the identity.
+ * format: 0 f32, 1 i16, 2 u16.  Every operation is exact for the integer formats.
+ * ------------------------------------------------------------------------------------------ */
+void aao_ingest(const void *pcm, int format, int channels, int64_t n_frames, float *out)
+{
+    const int use = channels < 2 ? channels : 2;
+    for (int64_t f = 0; f < n_frames; ++f) {
+        float acc = 0.0f;
+        for (int c = 0; c < use; ++c) {
+            const int64_t i = f * channels + c;
+            float v;
+            if (format == 1) v = (float)((const int16_t *)pcm)[i] / 32768.0f;
+            else if (format == 2) v = (float)(int16_t)((int32_t)((const uint16_t *)pcm)[i] - 32768) / 32768.0f;
+            else v = ((const float *)pcm)[i];
+            acc = acc + v;
+        }
+        out[f] = acc / (float)use;
+    }
+}

@@ -172,6 +172,7 @@ def lib():
     L.aao_interval.argtypes = [C.c_float, C.c_float, C.c_int, fp]
     ip = C.POINTER(C.c_int)
     L.aao_tuner_frame.argtypes = [fp, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, fp]
+    L.aao_ingest.argtypes = [vp, C.c_int, C.c_int, C.c_int64, fp]
     L.aao_cond_clip.restype = C.c_int64
     L.aao_cond_clip.argtypes = [C.POINTER(CondParams), fp, C.c_int64, vp, C.c_int]
     _lib = L
@@ -401,3 +402,16 @@ def tuner_frame(pairs, system: int = 0, single_pitch_mode: bool = False):
     lib().aao_tuner_frame(_fp(a), len(a), int(system), 1 if single_pitch_mode else 0, C.byref(k), C.byref(b),
                           C.byref(lo), C.byref(hi), C.byref(iv), C.byref(acc))
     return dict(kind=k.value, best=b.value, lo=lo.value, hi=hi.value, interval=iv.value, accuracy=acc.value)
+
+
+PCM_F32, PCM_I16, PCM_U16 = 0, 1, 2
+_PCM_DTYPES = {0: np.float32, 1: np.int16, 2: np.uint16}
+
+
+def ingest(pcm: np.ndarray, fmt: int, channels: int) -> np.ndarray:
+    """Input-callback conversion + downmix (mod.rs:765-792, dasp_sample 0.11.0): interleaved PCM -> mono f32."""
+    a = np.ascontiguousarray(pcm, _PCM_DTYPES[fmt]).reshape(-1)
+    n_frames = a.size // channels
+    out = np.zeros(n_frames, np.float32)
+    lib().aao_ingest(_vp(a), int(fmt), int(channels), n_frames, _fp(out))
+    return out

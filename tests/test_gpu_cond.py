@@ -153,3 +153,39 @@ def test_device_entry_point_and_edge_cases(aa, O, torch_cuda):
         aa.Conditioner(0.0, 1024)
     with pytest.raises(aa.AAError):
         cond.process_device(buf.data_ptr() + 4, 1, n, stride)
+
+
+def test_pcm_ingest_is_exact_and_analyze_host_pcm_equals_the_f32_path(aa, O, torch_cuda):
+    """mod.rs:765-792 on the device: bit-exact against the oracle for every format / channel count, and
+    aa_analyze_host_pcm(i16) == aa_analyze_host(the same samples as f32), byte for byte."""
+    torch = torch_cuda
+    rng = np.random.default_rng(12)
+    n_clips, clip_len = 5, 4096 + 8
+    for fmt, dt in ((aa.PCM_I16, np.int16), (aa.PCM_U16, np.uint16), (aa.PCM_F32, np.float32)):
+        for ch in (1, 2, 3):
+            if fmt == aa.PCM_F32:
+                pcm = rng.standard_normal((n_clips, clip_len * ch)).astype(np.float32)
+            else:
+                info = np.iinfo(dt)
+                pcm = rng.integers(info.min, info.max + 1, (n_clips, clip_len * ch)).astype(dt)
+            src = torch.from_numpy(pcm.view(np.uint8).reshape(-1).copy()).cuda()
+            out = torch.zeros(n_clips * clip_len, dtype=torch.float32, device="cuda")
+            aa.ingest_device(src.data_ptr(), fmt, ch, n_clips, clip_len, clip_len, clip_len, out.data_ptr(),
+                             torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            want = np.stack([O.ingest(row, fmt, ch) for row in pcm])
+            assert np.array_equal(out.cpu().numpy().reshape(n_clips, clip_len).view(np.uint32), want.view(np.uint32)), (fmt, ch)
+    # end to end: 16-bit stereo PCM through the host pipeline == the mixed-down f32 clips through aa_analyze_host
+    sr, n = 48000.0, 2048
+    clips = np.stack([signals.multitone(40 + i, sr, 20 * n) for i in range(6)])
+    l = np.clip(np.round(clips * 20000), -32768, 32767).astype(np.int16)
+    r = np.clip(np.round(clips[::-1] * 9000), -32768, 32767).astype(np.int16)
+    pcm = np.stack([l, r], axis=2).reshape(len(clips), -1)
+    mono = np.stack([O.ingest(row, aa.PCM_I16, 2) for row in pcm])
+    an = aa.Analyzer(aa.Config(n=n, sample_rate=sr))
+    a = an.analyze_host_pcm(pcm, aa.PCM_I16, 2)
+    b = an.analyze_host(mono)
+    for k in ("features", "stable", "mags", "summaries"):
+        assert a[k].tobytes() == b[k].tobytes(), k
+    with pytest.raises(aa.AAError):
+        an.analyze_host_pcm(pcm, 7, 2)

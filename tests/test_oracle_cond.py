@@ -255,3 +255,25 @@ def test_tuner_frame_branches(O):
     assert O.tuner_frame([[440.0, 0.4], [550.0, 0.9], [660.0, 0.9]])["kind"] == 3
     # SinglePitch mode: the highest score wins, the LAST one on ties (Iterator::max_by)
     assert O.tuner_frame([[440.0, 0.4], [550.0, 0.9], [660.0, 0.9]], 0, True)["best"] == 2
+
+
+# ---- input callback: device sample format -> mono f32 (mod.rs:765-792, dasp_sample 0.11.0) --------------
+
+def test_ingest_follows_the_published_conversions(O):
+    rng = np.random.default_rng(9)
+    i16 = rng.integers(-32768, 32768, 4096, dtype=np.int16)
+    i16[:4] = [-32768, 32767, 0, -1]
+    # dasp_sample: i16 -> f32 is s / 32768 (exact), u16 goes through i16
+    assert np.array_equal(O.ingest(i16, O.PCM_I16, 1), i16.astype(np.float32) / np.float32(32768.0))
+    u16 = (i16.astype(np.int32) + 32768).astype(np.uint16)
+    assert np.array_equal(O.ingest(u16, O.PCM_U16, 1), O.ingest(i16, O.PCM_I16, 1))
+    # stereo: (0 + l + r) / 2; more than two channels: only the first two are mixed (mod.rs:777, 786-791)
+    st = i16.reshape(-1, 2)
+    want = (st[:, 0].astype(np.float32) / 32768 + st[:, 1].astype(np.float32) / 32768) / np.float32(2)
+    assert np.array_equal(O.ingest(st, O.PCM_I16, 2), want)
+    quad = i16.reshape(-1, 4)
+    assert np.array_equal(O.ingest(quad, O.PCM_I16, 4), O.ingest(np.ascontiguousarray(quad[:, :2]), O.PCM_I16, 2))
+    f = rng.standard_normal(1024).astype(np.float32)
+    assert np.array_equal(O.ingest(f, O.PCM_F32, 1), f)
+    fs = f.reshape(-1, 2)
+    assert np.array_equal(O.ingest(fs, O.PCM_F32, 2), ((np.float32(0) + fs[:, 0]) + fs[:, 1]) / np.float32(2))
