@@ -10,8 +10,20 @@
 
 namespace aa {
 
+// These two kernels are HBM-bound: what matters is how many frames an SM has in flight, not the instruction
+// count.  The packed-arithmetic FFT core wants more registers (aligned pairs); capping the kernels at 64
+// registers keeps 1024 threads per SM resident (measured at n = 4096 / 2048 / 1024: 71 / 69 / 76 % of the HBM
+// peak without the cap, 76 / 70 / 95 % with it).  One-warp CTAs (n <= 512) are limited by the 32 CTAs an SM
+// can hold, not by registers, and lose with the cap.
 template <int N>
-__global__ void __launch_bounds__(N / 2 / Geo<N>::E) fft_forward_kernel(const float *__restrict__ in,
+constexpr int fft_min_blocks()
+{
+    constexpr int nt = N / 2 / Geo<N>::E;
+    return nt >= 64 ? 1024 / nt : 1;
+}
+
+template <int N>
+__global__ void __launch_bounds__(N / 2 / Geo<N>::E, fft_min_blocks<N>()) fft_forward_kernel(const float *__restrict__ in,
                                                                         int64_t batch,
                                                                         float *__restrict__ out, Tables tab)
 {
@@ -54,7 +66,7 @@ __global__ void __launch_bounds__(N / 2 / Geo<N>::E) fft_forward_kernel(const fl
 // inverse(forward(x)) == n * x; the imaginary parts of bins 0 and n/2 are ignored.
 // Computed as conj(FFT(conj(Zin))) with Zin rebuilt from the half spectrum.
 template <int N>
-__global__ void __launch_bounds__(N / 2 / Geo<N>::E) fft_inverse_kernel(const float *__restrict__ spec,
+__global__ void __launch_bounds__(N / 2 / Geo<N>::E, fft_min_blocks<N>()) fft_inverse_kernel(const float *__restrict__ spec,
                                                                         int64_t batch,
                                                                         float *__restrict__ out, Tables tab)
 {
