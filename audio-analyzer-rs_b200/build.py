@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libaa_gpu.so")
 SOURCES = ["aa_analyze.cu", "aa_fft_batch.cu", "aa_misc.cu", "aa_yin.cu", "aa_cond.cu", "aa_api.cu"]
-HEADERS = ["aa_fft.cuh", "aa_internal.h", os.path.join("..", "..", "include", "aa_gpu.h")]
+HEADERS = ["aa_fft.cuh", "aa_tma.cuh", "aa_internal.h", os.path.join("..", "..", "include", "aa_gpu.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

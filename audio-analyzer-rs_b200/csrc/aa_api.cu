@@ -236,8 +236,8 @@ extern "C" AA_API aa_status aa_fft_forward_device(aa_fft *h, const float *in_dev
                                                   float *out_dev, void *stream)
 {
     if (!h || !in_dev || !out_dev || batch < 0) return fail(AA_ERR_INVALID, "aa_fft_forward_device: bad argument");
-    if (((uintptr_t)in_dev & 7u) || ((uintptr_t)out_dev & 7u))
-        return fail(AA_ERR_INVALID, "aa_fft_forward_device: buffers must be 8-byte aligned");
+    if (((uintptr_t)in_dev & 15u) || ((uintptr_t)out_dev & 7u))
+        return fail(AA_ERR_INVALID, "aa_fft_forward_device: input must be 16-byte aligned (TMA bulk copy), output 8-byte");
     CU(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;   // NULL = the CUDA default stream
     CU(launch_fft_forward(h->n, h->dt.tab, in_dev, batch, out_dev, h->num_sms, s));

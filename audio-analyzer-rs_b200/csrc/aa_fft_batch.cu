@@ -7,6 +7,7 @@
 // split post-pass, coalesced float2 stores of the n/2+1 bins.
 #include "aa_fft.cuh"
 #include "aa_internal.h"
+#include "aa_tma.cuh"
 
 namespace aa {
 
@@ -22,23 +23,73 @@ constexpr int fft_min_blocks()
     return nt >= 64 ? 1024 / nt : 1;
 }
 
+// Forward transform.  Optionally the next frame's samples are fetched while the current frame is transformed:
+// one thread issues a TMA bulk copy (cp.async.bulk + mbarrier) into a staging buffer as soon as every thread has
+// pulled the current frame into registers (right after the first barrier of the FFT), so the HBM read latency
+// is hidden behind the arithmetic instead of being paid once per frame and CTA.  Measured per length (fraction
+// of the HBM peak, plain / staged): n = 4096 0.76 / 0.72, n = 2048 0.70 / 0.74, n = 1024 0.95 / 0.91 -- the
+// staging pass costs shared-memory bandwidth, so it is kept only where it wins.
+template <int N>
+struct FwdLayout {
+    static constexpr int N2 = N / 2;
+    static constexpr int NT = N2 / Geo<N>::E;
+    static constexpr bool STAGE = N == 2048;
+    static constexpr int EXLEN = (padded_len(N2) + 1) & ~1;
+    static constexpr size_t ex_bytes = sizeof(float2) * EXLEN;
+    static constexpr size_t stage_off = 2 * ex_bytes;                       // float[N] (16-byte aligned: EXLEN is even)
+    static constexpr size_t total = stage_off + (STAGE ? sizeof(float) * N : 0);
+};
+
 template <int N>
 __global__ void __launch_bounds__(N / 2 / Geo<N>::E, fft_min_blocks<N>()) fft_forward_kernel(const float *__restrict__ in,
                                                                         int64_t batch,
                                                                         float *__restrict__ out, Tables tab)
 {
+    using FL = FwdLayout<N>;
     constexpr int N2 = N / 2, E = Geo<N>::E, NT = N2 / E, EH = E / 2, HALF = N2 + 1, CBIN = N2 / 2;
-    constexpr int EXLEN = (padded_len(N2) + 1) & ~1;
-    __shared__ __align__(16) float2 exA[EXLEN];
-    __shared__ __align__(16) float2 exB[EXLEN];
+    constexpr bool STAGE = FL::STAGE;
+    extern __shared__ __align__(16) unsigned char fsm[];
+    float2 *exA = reinterpret_cast<float2 *>(fsm);
+    float2 *exB = reinterpret_cast<float2 *>(fsm + FL::ex_bytes);
+    float *stage = reinterpret_cast<float *>(fsm + FL::stage_off);
+    __shared__ __align__(8) uint64_t bar;
     const int t = threadIdx.x;
+    uint32_t phase = 0;
+    if (STAGE) {
+        if (t == 0) {
+            mbar_init(&bar, 1);
+            fence_proxy_async();
+        }
+        __syncthreads();
+        if (t == 0 && (int64_t)blockIdx.x < batch) {
+            mbar_expect_tx(&bar, N * 4);
+            bulk_g2s(stage, in + (int64_t)blockIdx.x * N, N * 4, &bar);
+        }
+    }
 
     for (int64_t fr = blockIdx.x; fr < batch; fr += gridDim.x) {
-        const float2 *src = reinterpret_cast<const float2 *>(in + fr * N);
         float2 v[E];
+        if (STAGE) {
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+            const float2 *src = reinterpret_cast<const float2 *>(stage);
 #pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = __ldg(&src[t + m * NT]);
-        fft_half_complex<N>(v, t, exA, exB, tab.tw);
+            for (int m = 0; m < E; ++m) v[m] = src[t + m * NT];
+        } else {
+            const float2 *src = reinterpret_cast<const float2 *>(in + fr * N);
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = __ldg(&src[t + m * NT]);
+        }
+        fft_run<N2, E, 1, 0>(
+            v, t, exA, exB, tab.tw, [] { __syncthreads(); },
+            [&] {
+                // every thread holds its samples in registers: the staging buffer can take the next frame
+                const int64_t nxt = fr + gridDim.x;
+                if (STAGE && t == 0 && nxt < batch) {
+                    mbar_expect_tx(&bar, N * 4);
+                    bulk_g2s(stage, in + nxt * N, N * 4, &bar);
+                }
+            });
 
         float2 *pbuf = ((fft_num_passes(N2, E) - 1) & 1) ? exB : exA;
 #pragma unroll
@@ -120,7 +171,17 @@ static cudaError_t launch_fwd(const Tables &tab, const float *in, int64_t batch,
     if (per_sm > 16) per_sm = 16;
     int64_t grid = (int64_t)num_sms * per_sm;
     if (grid > batch) grid = batch;
-    fft_forward_kernel<N><<<(unsigned)grid, NT, 0, s>>>(in, batch, out, tab);
+    using FL = FwdLayout<N>;
+    static unsigned long long configured = 0ull;     // the opt-in shared-memory size is a per-device attribute
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (FL::total > 48 * 1024 && (dev >= 64 || !((configured >> dev) & 1ull))) {
+        e = cudaFuncSetAttribute(fft_forward_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL::total);
+        if (e != cudaSuccess) return e;
+        if (dev < 64) configured |= 1ull << dev;
+    }
+    fft_forward_kernel<N><<<(unsigned)grid, NT, FL::total, s>>>(in, batch, out, tab);
     return cudaGetLastError();
 }
 
