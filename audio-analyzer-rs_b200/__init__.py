@@ -29,6 +29,8 @@ from ._ffi import (  # noqa: F401
     FLAG_FLUX_ONSET,
     FLAG_ONSET_FIRED,
     NOTE_NAMES,
+    ONSET_EVENT_DTYPE,
+    onset_events,
     PCM_F32,
     PCM_I16,
     PCM_U16,

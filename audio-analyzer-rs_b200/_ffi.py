@@ -186,6 +186,8 @@ def lib():
         "aa_notes_from_stable_host": (i32, [vp, i64, f32, vp]),
         "aa_ingest_device": (i32, [vp, i32, i32, i64, i64, i64, i64, vp, vp]),
         "aa_analyze_host_pcm": (i32, [vp, vp, i32, i32, i64, i64, i64, vp, C.POINTER(_Outputs)]),
+        "aa_onset_events_device": (i32, [C.POINTER(Config), vp, i64, i64, f32, i32, vp, vp, vp]),
+        "aa_onset_events_host": (i32, [C.POINTER(Config), vp, i64, i64, f32, i32, vp, vp]),
         "aa_tuner_from_stable_device": (i32, [vp, i64, f32, i32, i32, vp, vp]),
         "aa_tuner_from_stable_host": (i32, [vp, i64, f32, i32, i32, vp]),
         "aa_conditioner_create": (i32, [C.POINTER(CondConfig), pvp]),
@@ -555,3 +557,20 @@ def ingest_device(pcm_ptr: int, fmt: int, channels: int, n_clips: int, clip_len:
     """aa_ingest_device: interleaved PCM (f32 / i16 / u16) -> mono f32 clips (mod.rs:765-792)."""
     _check(lib().aa_ingest_device(C.c_void_p(pcm_ptr), int(fmt), int(channels), n_clips, clip_len, in_stride, out_stride,
                                   C.c_void_p(out_ptr), C.c_void_p(stream) if stream else None))
+
+
+ONSET_EVENT_DTYPE = np.dtype([("beat_position", "<f8"), ("sample_position", "<i8"), ("frame", "<i8"),
+                              ("velocity", "<f4"), ("reserved", "<u4")])
+assert ONSET_EVENT_DTYPE.itemsize == 32
+
+
+def onset_events(cfg: Config, features: np.ndarray, clip_len: int, bpm: float = 120.0, max_events: int = 256):
+    """Offline OnsetEvent lists (onset.rs:383-456 + timing.rs:311-337) from feature records [n_clips, T]:
+    returns (events [n_clips, max_events], counts [n_clips])."""
+    f = np.ascontiguousarray(np.atleast_2d(features), FEATURES_DTYPE)
+    n_clips = f.shape[0]
+    ev = np.zeros((n_clips, max_events), ONSET_EVENT_DTYPE)
+    cnt = np.zeros(n_clips, np.int32)
+    _check(lib().aa_onset_events_host(C.byref(cfg), _ptr(f), n_clips, int(clip_len), float(bpm), int(max_events),
+                                      _ptr(ev), _ptr(cnt)))
+    return ev, cnt

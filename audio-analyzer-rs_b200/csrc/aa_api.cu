@@ -1191,3 +1191,62 @@ extern "C" AA_API aa_status aa_tuner_from_stable_host(const aa_stable_pitches *s
     if (e != cudaSuccess) return fail_cuda(e, "aa_tuner_from_stable_host");
     return AA_OK;
 }
+
+// ---------------------------------------------------------------------------
+// offline onset events: onset.rs:383-456, timing.rs:311-337
+// ---------------------------------------------------------------------------
+static aa_status onset_events_check(const aa_config *cfg, int64_t n_clips, int64_t clip_len, float bpm, int32_t max_events,
+                                    int64_t *T)
+{
+    if (!cfg || n_clips < 0 || clip_len < 0 || !(bpm > 0.0f) || max_events < 1 || cfg->n <= 0 || cfg->hop <= 0 ||
+        !(cfg->sample_rate > 0.0f))
+        return fail(AA_ERR_INVALID, "aa_onset_events: bad argument");
+    *T = aa_num_frames(cfg, clip_len);
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_onset_events_device(const aa_config *cfg, const aa_frame_features *features_dev,
+                                                   int64_t n_clips, int64_t clip_len, float bpm, int32_t max_events,
+                                                   aa_onset_event *events_dev, int32_t *counts_dev, void *stream)
+{
+    int64_t T = 0;
+    aa_status st = onset_events_check(cfg, n_clips, clip_len, bpm, max_events, &T);
+    if (st != AA_OK) return st;
+    if (!features_dev || !events_dev || !counts_dev) return fail(AA_ERR_INVALID, "aa_onset_events_device: null pointer");
+    st = check_device(nullptr);
+    if (st != AA_OK) return st;
+    const double bps = (double)bpm / (60.0 * (double)cfg->sample_rate);                 // timing.rs:313-315
+    CU(launch_onset_events(features_dev, n_clips, T, cfg->n, cfg->hop, bps, max_events, events_dev, counts_dev,
+                           (cudaStream_t)stream));
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_onset_events_host(const aa_config *cfg, const aa_frame_features *features_host,
+                                                 int64_t n_clips, int64_t clip_len, float bpm, int32_t max_events,
+                                                 aa_onset_event *events_host, int32_t *counts_host)
+{
+    int64_t T = 0;
+    aa_status st = onset_events_check(cfg, n_clips, clip_len, bpm, max_events, &T);
+    if (st != AA_OK) return st;
+    if (!features_host || !events_host || !counts_host) return fail(AA_ERR_INVALID, "aa_onset_events_host: null pointer");
+    if (n_clips == 0) return AA_OK;
+    st = check_device(nullptr);
+    if (st != AA_OK) return st;
+    const size_t nf = (size_t)(n_clips * T), ne = (size_t)n_clips * (size_t)max_events;
+    aa_frame_features *d_f = nullptr;
+    aa_onset_event *d_e = nullptr;
+    int32_t *d_c = nullptr;
+    cudaError_t e = cudaMalloc(&d_f, std::max<size_t>(nf, 1) * sizeof(aa_frame_features));
+    if (e == cudaSuccess) e = cudaMalloc(&d_e, ne * sizeof(aa_onset_event));
+    if (e == cudaSuccess) e = cudaMalloc(&d_c, (size_t)n_clips * sizeof(int32_t));
+    if (e == cudaSuccess && nf) e = cudaMemcpy(d_f, features_host, nf * sizeof(aa_frame_features), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_e, 0, ne * sizeof(aa_onset_event));
+    if (e == cudaSuccess)
+        e = launch_onset_events(d_f, n_clips, T, cfg->n, cfg->hop, (double)bpm / (60.0 * (double)cfg->sample_rate),
+                                max_events, d_e, d_c, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(events_host, d_e, ne * sizeof(aa_onset_event), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(counts_host, d_c, (size_t)n_clips * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d_f); cudaFree(d_e); cudaFree(d_c);
+    if (e != cudaSuccess) return fail_cuda(e, "aa_onset_events_host");
+    return AA_OK;
+}

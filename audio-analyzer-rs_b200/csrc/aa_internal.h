@@ -80,6 +80,9 @@ cudaError_t launch_cond_agc(const float *stats, int64_t n_clips, int64_t n_slots
 cudaError_t launch_cond_apply_gain(float *clips, int64_t n_clips, int64_t clip_stride, int64_t n_slots, int slot_len,
                                    const float *gains, int num_sms, cudaStream_t s);
 
+cudaError_t launch_onset_events(const aa_frame_features *feat, int64_t n_clips, int64_t T, int n, int hop,
+                                double beats_per_sample, int max_events, aa_onset_event *events, int32_t *counts,
+                                cudaStream_t s);
 cudaError_t launch_ingest(const void *pcm, int format, int channels, int64_t n_clips, int64_t clip_len,
                           int64_t in_stride, int64_t out_stride, float *out, int num_sms, cudaStream_t s);
 cudaError_t launch_tuner(const aa_stable_pitches *stable, int64_t n_frames, float base_c0, int system,

@@ -171,6 +171,61 @@ cudaError_t launch_tuner(const aa_stable_pitches *stable, int64_t n_frames, floa
 }
 
 // ---------------------------------------------------------------------------
+// Offline onset events: the frames whose gating passed (AA_FLAG_ONSET_FIRED, onset.rs:383-456
+// without a live transport) compacted per clip into the OnsetEvent list the reference pushes on onset_tx, stamped
+// like MusicalTransport::stamp_onset (timing.rs:311-337) with zero latencies and the clip start as time zero.
+// One warp per clip: ballot + prefix over 32 frames at a time keeps the events in time order.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) onset_events_kernel(const aa_frame_features *__restrict__ feat, int64_t n_clips,
+                                                           int64_t T, int n, int hop, double beats_per_sample,
+                                                           int max_events, aa_onset_event *__restrict__ events,
+                                                           int32_t *__restrict__ counts)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t clip = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (clip >= n_clips) return;
+    const aa_frame_features *f = feat + clip * T;
+    aa_onset_event *out = events + clip * (int64_t)max_events;
+    int cnt = 0;
+    for (int64_t base = 0; base < T; base += 32) {
+        const int64_t fr = base + lane;
+        bool fired = false;
+        float flux = 0.f, maxex = 0.f;
+        if (fr < T) {
+            fired = (f[fr].flags & AA_FLAG_ONSET_FIRED) != 0u;
+            flux = f[fr].flux;
+            maxex = f[fr].max_excess;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, fired);
+        const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+        if (fired && pos < max_events) {
+            float v = __fdiv_rn(fmaxf(flux, __fmul_rn(maxex, 5.0f)), 50.0f);       // onset.rs:388-390
+            v = fminf(fmaxf(v, 0.0f), 1.0f);
+            aa_onset_event e;
+            e.sample_position = fr * (int64_t)hop + n / 2;                         // window centre, onset.rs:386-387
+            e.beat_position = (double)e.sample_position * beats_per_sample;        // timing.rs:313-326
+            e.frame = fr;
+            e.velocity = v;
+            e.reserved = 0u;
+            out[pos] = e;
+        }
+        cnt += __popc(bal);
+    }
+    if (lane == 0) counts[clip] = cnt;
+}
+
+cudaError_t launch_onset_events(const aa_frame_features *feat, int64_t n_clips, int64_t T, int n, int hop,
+                                double beats_per_sample, int max_events, aa_onset_event *events, int32_t *counts,
+                                cudaStream_t s)
+{
+    if (n_clips <= 0) return cudaSuccess;
+    const int wpb = 4;
+    const unsigned grid = (unsigned)((n_clips + wpb - 1) / wpb);
+    onset_events_kernel<<<grid, wpb * 32, 0, s>>>(feat, n_clips, T, n, hop, beats_per_sample, max_events, events, counts);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // Synthetic clips.
 // ---------------------------------------------------------------------------
 __host__ __device__ inline uint64_t splitmix64(uint64_t &x)

@@ -216,6 +216,28 @@ AA_API aa_status aa_notes_from_stable_device(const aa_stable_pitches *stable_dev
 AA_API aa_status aa_notes_from_stable_host(const aa_stable_pitches *stable_host, int64_t n_frames,
                                            float base_freq, aa_note_record *notes_host);
 
+/* Offline onset events.  For every frame with AA_FLAG_ONSET_FIRED -- the offline reading of the
+ * gating in OnsetDetector::detect_onsets (src/analysis/onset.rs:383-456: no metronome ticks to guard against,
+ * calibration done) -- the OnsetEvent (src/audio_io/timing.rs:77-87) the reference would push on onset_tx, stamped
+ * like MusicalTransport::stamp_onset (timing.rs:311-337) with zero input / output latency and calibration and the
+ * clip start as time zero: velocity = clamp(max(flux, 5 max_excess) / 50, 0, 1) (onset.rs:388-390),
+ * sample_position = frame * hop + n / 2 (the window centre), beat_position = sample_position * bpm / (60 sr).
+ * events: [n_clips][max_events] in time order; counts[c] is the number of fired frames of clip c (it may exceed
+ * max_events, in which case only the first max_events were written). */
+typedef struct aa_onset_event {           /* 32 bytes */
+    double   beat_position;
+    int64_t  sample_position;
+    int64_t  frame;
+    float    velocity;
+    uint32_t reserved;
+} aa_onset_event;
+AA_API aa_status aa_onset_events_device(const aa_config *cfg, const aa_frame_features *features_dev, int64_t n_clips,
+                                        int64_t clip_len, float bpm, int32_t max_events, aa_onset_event *events_dev,
+                                        int32_t *counts_dev, void *stream);
+AA_API aa_status aa_onset_events_host(const aa_config *cfg, const aa_frame_features *features_host, int64_t n_clips,
+                                      int64_t clip_len, float bpm, int32_t max_events, aa_onset_event *events_host,
+                                      int32_t *counts_host);
+
 /* Tuner::run's per-frame branch (src/analysis/tuner.rs:148-193) with Interval::new
  * (src/analysis/theory.rs:306-382) on the stable pitches: numeric form of TunerOutput.label / .cents
  * (the strings stay on the host).  system: 0 EqualTemperament, 1 JustIntonation, 2 Pythagorean

@@ -216,6 +216,16 @@ void      aao_cond_destroy(aao_cond *c);
 void      aao_cond_reset(aao_cond *c);
 void      aao_cond_filter_gate(aao_cond *c, float *slot, int len);
 void      aao_cond_agc(aao_cond *c, float *slot, int len, aao_dynamics *out, int apply);
+/* one onset event of an offline clip; 32 bytes, identical layout to aa_onset_event */
+typedef struct aao_onset_event {
+    double   beat_position;
+    int64_t  sample_position;
+    int64_t  frame;
+    float    velocity;
+    uint32_t reserved;
+} aao_onset_event;
+int64_t   aao_onset_events(const aao_features *feat, int64_t T, int n, int hop, float sample_rate, float bpm,
+                           int64_t max_events, aao_onset_event *out);
 int       aao_interval(float f_lo, float f_hi, int system, float *accuracy);
 void      aao_tuner_frame(const float *pairs, int n, int system, int single_pitch_mode, int *kind, int *best, int *lo,
                           int *hi, int *interval, float *accuracy);

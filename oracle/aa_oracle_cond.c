@@ -338,3 +338,37 @@ void aao_ingest(const void *pcm, int format, int channels, int64_t n_frames, flo
         out[f] = acc / (float)use;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Offline onset events: what OnsetDetector pushes on onset_tx for every frame whose
+ * gating passed (onset.rs:383-456 with no metronome ticks and calibration done = AAO_FLAG_ONSET_FIRED),
+ * stamped like MusicalTransport::stamp_onset (timing.rs:311-337) with zero latencies / calibration and the
+ * clip start as time zero:
+ *   velocity        = clamp(max(flux, max_excess * 5) / 50, 0, 1)            onset.rs:388-390 (f32)
+ *   sample_position = frame * hop + n / 2   (the window centre, onset.rs:386-387)
+ *   beat_position   = sample_position * bpm / (60 * sr)                       timing.rs:313-326 (f64)
+ * Returns the number of events of the clip (all of them are counted, at most max_events are written).
+ * ------------------------------------------------------------------------------------------ */
+int64_t aao_onset_events(const aao_features *feat, int64_t T, int n, int hop, float sample_rate, float bpm,
+                         int64_t max_events, aao_onset_event *out)
+{
+    const double beats_per_sample = (double)bpm / (60.0 * (double)sample_rate);
+    int64_t cnt = 0;
+    for (int64_t f = 0; f < T; ++f) {
+        if (!(feat[f].flags & AAO_FLAG_ONSET_FIRED)) continue;
+        if (cnt < max_events) {
+            float v = fmaxf(feat[f].flux, feat[f].max_excess * 5.0f) / 50.0f;
+            if (v < 0.0f) v = 0.0f;
+            if (v > 1.0f) v = 1.0f;
+            aao_onset_event e;
+            e.sample_position = f * (int64_t)hop + n / 2;
+            e.beat_position = (double)e.sample_position * beats_per_sample;
+            e.frame = f;
+            e.velocity = v;
+            e.reserved = 0;
+            out[cnt] = e;
+        }
+        ++cnt;
+    }
+    return cnt;
+}

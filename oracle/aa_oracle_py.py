@@ -173,6 +173,8 @@ def lib():
     ip = C.POINTER(C.c_int)
     L.aao_tuner_frame.argtypes = [fp, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, fp]
     L.aao_ingest.argtypes = [vp, C.c_int, C.c_int, C.c_int64, fp]
+    L.aao_onset_events.restype = C.c_int64
+    L.aao_onset_events.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int64, vp]
     L.aao_cond_clip.restype = C.c_int64
     L.aao_cond_clip.argtypes = [C.POINTER(CondParams), fp, C.c_int64, vp, C.c_int]
     _lib = L
@@ -415,3 +417,16 @@ def ingest(pcm: np.ndarray, fmt: int, channels: int) -> np.ndarray:
     out = np.zeros(n_frames, np.float32)
     lib().aao_ingest(_vp(a), int(fmt), int(channels), n_frames, _fp(out))
     return out
+
+
+ONSET_EVENT_DTYPE = np.dtype([("beat_position", "<f8"), ("sample_position", "<i8"), ("frame", "<i8"),
+                              ("velocity", "<f4"), ("reserved", "<u4")])
+assert ONSET_EVENT_DTYPE.itemsize == 32
+
+
+def onset_events(features: np.ndarray, n: int, hop: int, sample_rate: float, bpm: float = 120.0, max_events: int = 256):
+    """Offline onset event list of one clip (onset.rs:383-456 + timing.rs:311-337): (events, total count)."""
+    f = np.ascontiguousarray(features, FEATURES_DTYPE)
+    out = np.zeros(max_events, ONSET_EVENT_DTYPE)
+    cnt = lib().aao_onset_events(_vp(f), len(f), int(n), int(hop), float(sample_rate), float(bpm), int(max_events), _vp(out))
+    return out[: min(cnt, max_events)], int(cnt)

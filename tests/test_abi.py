@@ -100,3 +100,8 @@ def test_conditioner_boundary(aa, O):
         with pytest.raises(aa.AAError) as e:
             aa.Conditioner(*bad)
         assert e.value.code == -1
+
+
+def test_new_record_layouts(aa, O):
+    assert aa.ONSET_EVENT_DTYPE.itemsize == 32 and aa.ONSET_EVENT_DTYPE == O.ONSET_EVENT_DTYPE
+    assert aa.TUNER_RECORD_DTYPE.itemsize == 16

@@ -424,3 +424,28 @@ def test_tuner_records_match_the_reference_branches(aa, O, torch_cuda):
     assert aa.INT_TYPES[aa.tuner_from_stable(st[:13], 440.0, 0, False)["interval"][7]] == "Per5"
     with pytest.raises(aa.AAError):
         aa.tuner_from_stable(st, 440.0, 3, False)
+
+
+def test_offline_onset_events(aa, O, torch_cuda):
+    """aa_onset_events_* (SURVEY 8f rank 3): fired frames compacted into OnsetEvent lists; bit-exact against the
+    oracle restatement of onset.rs:386-390 + timing.rs:311-337 (velocity in f32, beat position in f64)."""
+    sr, n = 48000.0, 1024
+    hop = n // 4
+    clips = np.stack([signals.note_sequence(60 + i, sr, 96000, n_notes=10) for i in range(9)])
+    clips[8] *= 0.0
+    cfg = aa.Config(n=n, sample_rate=sr)
+    res = aa.Analyzer(cfg).analyze_host(clips, want_mags=False)
+    ev, cnt = aa.onset_events(cfg, res["features"], clips.shape[1], bpm=97.5, max_events=64)
+    fired = (res["features"]["flags"] & aa.FLAG_ONSET_FIRED) != 0
+    assert np.array_equal(cnt, fired.sum(axis=1)) and cnt[8] == 0 and cnt[:8].min() >= 3
+    for c in range(len(clips)):
+        want, total = O.onset_events(res["features"][c], n, hop, sr, 97.5, 64)
+        assert total == cnt[c]
+        assert ev[c][: cnt[c]].tobytes() == want.tobytes()
+        assert np.array_equal(ev[c]["frame"][: cnt[c]], np.nonzero(fired[c])[0])
+        assert np.all(ev[c]["sample_position"][: cnt[c]] == ev[c]["frame"][: cnt[c]] * hop + n // 2)
+    # truncation: counts keep the total, only max_events are written (the earliest ones)
+    ev2, cnt2 = aa.onset_events(cfg, res["features"], clips.shape[1], bpm=97.5, max_events=2)
+    assert np.array_equal(cnt2, cnt) and ev2[0].tobytes() == ev[0][:2].tobytes()
+    with pytest.raises(aa.AAError):
+        aa.onset_events(cfg, res["features"], clips.shape[1], bpm=0.0)
