@@ -294,11 +294,13 @@ def run_ours(a):
         # The same call on 16-bit mono PCM (the reference's input callback takes i16 devices too, mod.rs:691):
         # the samples are the batch quantised to i16, converted on the device (aa_analyze_host_pcm), so the
         # PCIe-bound path moves half the bytes.  Reported beside e2e, not instead of it.
-        h_pcm = aa.pinned_empty((n_clips, clip_len), np.int16)
         np.multiply(h_clips, 32767.0, out=h_clips)
         np.rint(h_clips, out=h_clips)
-        h_pcm[...] = h_clips
-        del h_clips
+        tmp16 = h_clips.astype(np.int16)         # pageable; the pinned f32 buffer is released before the
+        del h_clips                              # pinned i16 buffer is allocated (8 ranks share one host)
+        h_pcm = aa.pinned_empty((n_clips, clip_len), np.int16)
+        h_pcm[...] = tmp16
+        del tmp16
 
         def pcm_step():
             an.analyze_host_pcm_into(h_pcm, aa.PCM_I16, 1, n_clips, clip_len, clip_len, features=h_feat,
