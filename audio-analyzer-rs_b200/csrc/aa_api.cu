@@ -383,7 +383,10 @@ struct aa_analyzer {
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     StageSlot slot[2];
     unsigned char *scratch = nullptr;   // per-CTA overflow scratch of the analysis kernel
-    unsigned long long *work_counter = nullptr;   // clip queue of the persistent CTAs
+    unsigned long long *work_counter = nullptr;   // work queue of the persistent CTAs: [16 B counter][n_clips x 2 u32 flags]
+    size_t flag_clips_cap = 0;                    // clips the segment flags behind the counter have room for
+    float *seg_state = nullptr;                   // [n_clips][state_floats]: state hand-off between time segments
+    size_t seg_state_cap = 0;                     // in floats
     int max_grid = 0;
     int64_t launches = 0;
 };
@@ -412,7 +415,7 @@ extern "C" AA_API aa_status aa_analyzer_create(const aa_config *cfg, aa_analyzer
     }
     h->max_grid = sms * analyze_ctas_per_sm(cfg->n);
     if ((e = cudaMalloc(&h->scratch, (size_t)h->max_grid * analyze_scratch_bytes(cfg->n))) != cudaSuccess ||
-        (e = cudaMalloc(&h->work_counter, sizeof(unsigned long long))) != cudaSuccess) {
+        (e = cudaMalloc(&h->work_counter, 16)) != cudaSuccess) {
         aa_analyzer_destroy(h);
         return fail_cuda(e, "cudaMalloc(scratch)");
     }
@@ -446,12 +449,51 @@ extern "C" AA_API aa_status aa_analyzer_destroy(aa_analyzer *h)
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     cudaFree(h->scratch);
     cudaFree(h->work_counter);
+    cudaFree(h->seg_state);
     cudaFree(h->dt.mem);
     delete h;
     return AA_OK;
 }
 
 extern "C" AA_API int64_t aa_analyzer_last_launches(const aa_analyzer *h) { return h ? h->launches : 0; }
+
+template <typename Tp>
+static aa_status grow(Tp **p, size_t *cap, size_t need)
+{
+    if (need <= *cap) return AA_OK;
+    cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    CU(cudaMalloc(p, need * sizeof(Tp)));
+    *cap = need;
+    return AA_OK;
+}
+
+// Time segments of a clip for the batch path (see AnalyzeParams::n_seg).  With more clips than resident CTAs the
+// clips are dealt from a queue, and a batch ends with CTAs idling for up to one clip while the last ones finish
+// (1024 clips on 444 CTAs: 5-6 % of the run).  Cutting the clips into segments that halve towards the end makes
+// that ragged end one short segment; a segment costs one state hand-off through HBM (33 KB each way at n = 4096)
+// and a refill of the hop ring.  AA_SEG_MIN (frames, environment, read once) overrides the shortest segment;
+// 0 turns segmentation off.
+static int plan_segments(int64_t T, int64_t n_clips, int grid, int *start)
+{
+    static const int min_seg = [] {
+        const char *e = getenv("AA_SEG_MIN");
+        return e ? atoi(e) : 32;
+    }();
+    start[0] = 0;
+    start[1] = (int)T;
+    if (min_seg <= 0 || n_clips <= grid || n_clips >= 16 * (int64_t)grid) return 1;
+    int n = 0;
+    int64_t pos = 0;
+    while (n < aa::AA_MAX_SEG - 1 && T - pos > 2 * (int64_t)min_seg) {
+        start[n++] = (int)pos;
+        pos += (T - pos) / 2;
+    }
+    start[n++] = (int)pos;
+    start[n] = (int)T;
+    return n;
+}
 
 static aa_status analyze_device_impl(aa_analyzer *h, const float *clips_dev, int64_t n_clips, int64_t clip_len,
                                      int64_t clip_stride, const uint8_t *onset_in_dev, const aa_outputs *out,
@@ -484,8 +526,25 @@ static aa_status analyze_device_impl(aa_analyzer *h, const float *clips_dev, int
     // more clips than resident CTAs: hand them out through a device-wide queue so that every SM ends up
     // with the same amount of work to within one clip
     p.work_counter = nullptr;
+    p.n_seg = 1;
+    p.seg_start[0] = 0;
+    p.seg_start[1] = (int)T;
     if (n_clips > p.grid) {
-        CU(cudaMemsetAsync(h->work_counter, 0, sizeof(unsigned long long), s));
+        if (!state) p.n_seg = plan_segments(T, n_clips, p.grid, p.seg_start);
+        if (p.n_seg > 1) {
+            if ((size_t)n_clips > h->flag_clips_cap) {
+                cudaFree(h->work_counter);
+                h->work_counter = nullptr;
+                h->flag_clips_cap = 0;
+                CU(cudaMalloc(&h->work_counter, 16 + (size_t)n_clips * 2 * sizeof(unsigned)));
+                h->flag_clips_cap = (size_t)n_clips;
+            }
+            aa_status st = grow(&h->seg_state, &h->seg_state_cap, (size_t)n_clips * state_floats(p.half));
+            if (st != AA_OK) return st;
+            p.seg_state = h->seg_state;
+            p.seg_flags = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(h->work_counter) + 16);
+        }
+        CU(cudaMemsetAsync(h->work_counter, 0, p.n_seg > 1 ? 16 + (size_t)n_clips * 2 * sizeof(unsigned) : 16, s));
         p.work_counter = h->work_counter;
     }
     CU(launch_analyze(p, s));
@@ -509,18 +568,6 @@ extern "C" AA_API aa_status aa_analyze_device(aa_analyzer *h, const float *clips
     cudaStream_t s = (cudaStream_t)stream;   // NULL = the CUDA default stream
     return analyze_device_impl(h, clips_dev, n_clips, clip_len, clip_stride, onset_in_dev, out_dev, nullptr, s,
                                &h->launches);
-}
-
-template <typename Tp>
-static aa_status grow(Tp **p, size_t *cap, size_t need)
-{
-    if (need <= *cap) return AA_OK;
-    cudaFree(*p);
-    *p = nullptr;
-    *cap = 0;
-    CU(cudaMalloc(p, need * sizeof(Tp)));
-    *cap = need;
-    return AA_OK;
 }
 
 // format / channels: what the host buffer holds (AA_PCM_*, interleaved); mono f32 is copied straight into the

@@ -24,6 +24,8 @@ struct Tables {
 //   float tracks[3][32]  : freq, score, life (as float)
 __host__ __device__ inline size_t state_floats(int half) { return (size_t)4 * half + 8 + 96; }
 
+constexpr int AA_MAX_SEG = 8;
+
 struct AnalyzeParams {
     const float *clips;
     int64_t n_clips, clip_len, clip_stride, T;
@@ -36,7 +38,16 @@ struct AnalyzeParams {
     float *state;            // [n_clips][state_floats(half)] or nullptr
     unsigned char *scratch;  // [grid][analyze_scratch_bytes(n)] overflow space for frames with > 256 candidates
     int grid;                // persistent CTAs: min(n_clips, num_sms * analyze_ctas_per_sm(n))
-    unsigned long long *work_counter;   // device-wide clip queue (zeroed before the launch) or nullptr = static
+    unsigned long long *work_counter;   // device-wide work queue (zeroed before the launch) or nullptr = static
+    // Time segments (batch mode with more clips than resident CTAs): a work item is (clip, segment), items are
+    // dealt segment-major from the queue, and a segment hands the analyzer state to the next one through
+    // seg_state[clip] -- the same state block the streaming API carries -- guarded by seg_flags[clip][0 / 1]
+    // ("segments whose main-warp / tail-warp state has been published", zeroed before the launch).  Segments
+    // get shorter towards the end of the clip, so the ragged end of the batch is one short segment, not one clip.
+    int n_seg;                          // 1 = whole clips
+    int seg_start[AA_MAX_SEG + 1];      // frame range of segment s: [seg_start[s], seg_start[s + 1])
+    float *seg_state;                   // [n_clips][state_floats(half)]
+    unsigned *seg_flags;                // [n_clips][2]
     Tables tab;
     int n, hop, half;
     float bin_width, min_freq, max_freq;

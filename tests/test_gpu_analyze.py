@@ -327,6 +327,48 @@ def test_full_size_cfg2_properties(aa, O, torch_cuda):
         assert (ref["features"]["burst_count"] != h_feat[c]["burst_count"]).mean() < 0.02
 
 
+def test_time_segments_equal_whole_clips(aa, O, torch_cuda):
+    """Batches with more clips than resident CTAs are cut into time segments that hand the analyzer state
+    (per-bin floors, previous magnitudes, FluxTracker / EMA scalars, PitchTracker tracks) through HBM.
+    Every output must be byte-identical to the same clips analysed whole: sub-batches of at most one clip
+    per resident CTA take the static, unsegmented path."""
+    torch = torch_cuda
+    for n, sr, n_clips, clip_len, n_distinct in ((1024, 48000.0, 1200, 1024 + 256 * 299, 5),
+                                                 (4096, 48000.0, 500, 4096 + 1024 * 200, 4)):
+        an = aa.Analyzer(aa.Config(n=n, sample_rate=sr))
+        T = an.num_frames(clip_len)
+        half = n // 2 + 1
+        base = np.stack([signals.multitone(40 + c, sr, clip_len) for c in range(n_distinct)])
+        clips = torch.from_numpy(base).cuda()[torch.arange(n_clips, device="cuda") % n_distinct].contiguous()
+        onset = (torch.arange(n_clips * T, device="cuda") % 37 == 5).to(torch.uint8)   # exercises the tracker's onset branch
+
+        def run(first, count):
+            feat = torch.zeros(count, T, 96, device="cuda", dtype=torch.uint8)
+            stab = torch.zeros(count, T, 136, device="cuda", dtype=torch.uint8)
+            mags = torch.zeros(count, T, half, device="cuda", dtype=torch.float32)
+            an.analyze_device(clips[first:first + count].data_ptr(), count, clip_len, clip_len,
+                              onset_in=onset[first * T:].data_ptr(), features=feat.data_ptr(),
+                              stable=stab.data_ptr(), mags=mags.data_ptr(),
+                              stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            return feat, stab, mags
+
+        feat, stab, mags = run(0, n_clips)                 # queue + segments (n_clips > resident CTAs)
+        sub = 148                                          # <= one clip per CTA on any B200 configuration
+        for first in range(0, n_clips, sub):
+            cnt = min(sub, n_clips - first)
+            f2, s2, m2 = run(first, cnt)
+            assert torch.equal(feat[first:first + cnt], f2), (n, first)
+            assert torch.equal(stab[first:first + cnt], s2), (n, first)
+            assert torch.equal(mags[first:first + cnt], m2), (n, first)
+        # and the whole-clip path agrees with the oracle on one clip (stage-isolated, pitch counts)
+        h_feat = feat[1].cpu().numpy().view(aa.FEATURES_DTYPE).reshape(T)
+        iso = O.analyze_clip(O.make_config(n, n // 4, sr), mags_in=mags[1].cpu().numpy(),
+                             onset_in=onset[T:2 * T].cpu().numpy())
+        assert (iso["features"]["burst_count"] == h_feat["burst_count"]).all()
+        assert (iso["features"]["n_pitches"] == h_feat["n_pitches"]).mean() > 0.97
+
+
 def test_note_records_match_reference_from_freq(aa, O, torch_cuda):
     """NEXT row f2: Note::from_freq (theory.rs:195-209) on the device for every stable pitch."""
     x = np.stack([signals.sine(440.0, 44100.0, 30000), signals.multitone(3, 44100.0, 30000)])
