@@ -126,7 +126,8 @@ __host__ __device__ constexpr int padoff(int d) { return d + (d >> 4); }
 // table load by a product tree of depth <= 4 (<= 4 extra roundings, far inside the magnitude
 // tolerance) instead of R-1 dependent L2-latency loads.  If !LAST the outputs are scattered into
 // `exch` (padded indexing); the caller synchronises and reloads with fft_reload().
-template <int N2, int E, int R, int NS, bool LAST>
+// TWS: the twiddle table belongs to a transform TWS times longer (sub-transforms of fft_run_split).
+template <int N2, int E, int R, int NS, bool LAST, int TWS = 1>
 __device__ __forceinline__ void fft_pass(float2 (&v)[E], int t, float2 *exch,
                                          const float2 *__restrict__ tw)
 {
@@ -141,7 +142,7 @@ __device__ __forceinline__ void fft_pass(float2 (&v)[E], int t, float2 *exch,
         for (int r = 0; r < R; ++r) x[r] = v[b + r * BPT];
         const int k = j & (NS - 1);
         if (NS > 1) {
-            constexpr int TSTEP = N2 / (NS * R);
+            constexpr int TSTEP = TWS * (N2 / (NS * R));
             float2 w[R];
             w[1] = __ldg(&tw[k * TSTEP]);
 #pragma unroll
@@ -231,6 +232,78 @@ __device__ __forceinline__ void fft_half_complex(float2 (&v)[Geo<N>::E], int t, 
                                                  float2 *exB, const float2 *__restrict__ tw)
 {
     fft_run<N / 2, Geo<N>::E, 1, 0>(v, t, exA, exB, tw, [] { __syncthreads(); }, [] {});
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Split plan for the fused analysis kernel (N2 = 8 * M, E = 8, NT = M threads): two block-wide exchanges
+// instead of one per Stockham pass.
+//   Z[k1 + 8 k2] = sum_t W_M^(t k2) * [ W_N2^(t k1) * sum_m z[t + M m] W_8^(m k1) ]
+//   1. thread t: radix-8 butterfly over its own v[m] = z[t + M m], then times W_N2^(t k1)      (registers)
+//   2. block exchange: sub-transform k1 (M points) goes to the G = M/8 consecutive threads k1*G .. k1*G + G - 1
+//      (one warp at N2 = 2048, half a warp at N2 = 1024)
+//   3. each group runs the M-point Stockham passes on its own region of exA; only __syncwarp() inside
+//   4. the results go to exB in natural order (block exchange), where the real-FFT post-pass finds both
+//      Z[k] and its partner Z[N2 - k]
+// `sync` is the block barrier, `after_first` runs right after the first one.  On return (after the second
+// barrier) exB[padidx(k)] = Z[k] for every k.
+template <int M>
+struct SplitGeo {
+    static constexpr int G = M / 8;                              // threads per sub-transform
+    static constexpr int RS = (padidx(M - 1) + 1 + 7) & ~7;      // float2 units per region (272 / 136)
+};
+
+template <int M, int NS, int TWS>
+__device__ __forceinline__ void fft_run_local(float2 (&v)[8], int tl, float2 *reg, const float2 *__restrict__ tw)
+{
+    constexpr int REM = M / NS;
+    constexpr int R = REM < 8 ? REM : 8;
+    constexpr bool LAST = (NS * R == M);
+    fft_pass<M, 8, R, NS, LAST, TWS>(v, tl, reg, tw);
+    if constexpr (!LAST) {
+        __syncwarp();
+        fft_reload<M, 8>(v, tl, reg);
+        __syncwarp();                        // the next pass writes the same region
+        fft_run_local<M, NS * R, TWS>(v, tl, reg, tw);
+    }
+}
+
+template <int N2, class Sync, class Hook>
+__device__ __forceinline__ void fft_run_split(float2 (&v)[8], int t, float2 *exA, float2 *exB,
+                                              const float2 *__restrict__ tw, Sync sync, Hook after_first)
+{
+    constexpr int M = N2 / 8, NT = M, G = SplitGeo<M>::G, RS = SplitGeo<M>::RS;
+    static_assert(G == 32 || G == 16, "a sub-transform must live inside one warp");
+    // 1. radix-8 over m (decimation in frequency), twiddles W_N2^(t k1) from one table load
+    Bfly<8>::run(v);
+    {
+        float2 w[8];
+        w[1] = __ldg(&tw[t]);
+#pragma unroll
+        for (int r = 2; r < 8; ++r) {
+            const int hi = r >= 4 ? 4 : 2;
+            const int lo = r - hi;
+            w[r] = lo ? cmul(w[hi], w[lo]) : cmul(w[hi / 2], w[hi / 2]);
+        }
+#pragma unroll
+        for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], w[r]);
+    }
+    // 2. to the groups
+#pragma unroll
+    for (int r = 0; r < 8; ++r) exA[r * RS + t] = v[r];
+    sync();
+    after_first();
+    const int k1 = t / G, tl = t % G;
+    float2 *reg = exA + k1 * RS;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = reg[tl + m * G];
+    __syncwarp();                            // the passes below scatter into the same region
+    // 3. M-point transform inside the group
+    fft_run_local<M, 1, 8>(v, tl, reg, tw);
+    // 4. v[m] = Z[k1 + 8 (tl + G m)] = Z[(k1 + 8 tl) + NT m], natural order in exB
+    float2 *dst = exB + padidx(k1 + 8 * tl);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) dst[padoff(m * NT)] = v[m];
+    sync();
 }
 
 // realfft's split post-pass for one pair: a = Z[k], b = Z[N/2 - k], tw = 0.5*exp(-2 pi i k/N).
