@@ -30,6 +30,29 @@ __device__ __forceinline__ float2 cmul_negi(float2 a) { return make_float2(a.y, 
 __device__ __forceinline__ float2 cmul_posi(float2 a) { return make_float2(-a.y, a.x); }  // a * (+i)
 __device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
 
+// Table loads (window, twiddles): read-only path.  With AA_TAB_EVICT_LAST the lines are marked evict-last in L1:
+// the fused analysis kernel leaves the SM only ~23 KB of L1, which the tables (~24 KB hot) share with the output
+// stores and whatever else passes through.
+__device__ __forceinline__ float2 ld_table(const float2 *p)
+{
+#ifdef AA_TAB_EVICT_LAST
+    float2 v;
+    asm("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+// streaming output store: with AA_ST_NO_ALLOCATE it does not allocate a line in L1
+__device__ __forceinline__ void st_stream(float *p, float v)
+{
+#ifdef AA_ST_NO_ALLOCATE
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+#else
+    *p = v;
+#endif
+}
+
 // exchange-buffer padding: one float2 every 16 keeps both the strided writes of the
 // first pass and the unit-stride reads at the ideal wavefront count.
 __host__ __device__ __forceinline__ constexpr int padidx(int i) { return i + (i >> 4); }
@@ -144,7 +167,7 @@ __device__ __forceinline__ void fft_pass(float2 (&v)[E], int t, float2 *exch,
         if (NS > 1) {
             constexpr int TSTEP = TWS * (N2 / (NS * R));
             float2 w[R];
-            w[1] = __ldg(&tw[k * TSTEP]);
+            w[1] = ld_table(&tw[k * TSTEP]);
 #pragma unroll
             for (int r = 2; r < R; ++r) {
                 const int hi = (r >= 8) ? 8 : (r >= 4 ? 4 : 2);   // largest power of two <= r
