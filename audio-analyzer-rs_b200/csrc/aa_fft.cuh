@@ -150,9 +150,11 @@ __host__ __device__ constexpr int padoff(int d) { return d + (d >> 4); }
 // tolerance) instead of R-1 dependent L2-latency loads.  If !LAST the outputs are scattered into
 // `exch` (padded indexing); the caller synchronises and reloads with fft_reload().
 // TWS: the twiddle table belongs to a transform TWS times longer (sub-transforms of fft_run_split).
-template <int N2, int E, int R, int NS, bool LAST, int TWS = 1>
+// PRE: the butterflies' first twiddles w^1 were loaded by the caller (w1pre[b]) -- fft_run issues them before
+// the barrier in front of the pass, so a load that misses L1 overlaps the barrier wait and the reload.
+template <int N2, int E, int R, int NS, bool LAST, int TWS = 1, bool PRE = false>
 __device__ __forceinline__ void fft_pass(float2 (&v)[E], int t, float2 *exch,
-                                         const float2 *__restrict__ tw)
+                                         const float2 *__restrict__ tw, const float2 *w1pre = nullptr)
 {
     constexpr int NT = N2 / E;
     constexpr int BPT = E / R;
@@ -167,7 +169,7 @@ __device__ __forceinline__ void fft_pass(float2 (&v)[E], int t, float2 *exch,
         if (NS > 1) {
             constexpr int TSTEP = TWS * (N2 / (NS * R));
             float2 w[R];
-            w[1] = ld_table(&tw[k * TSTEP]);
+            w[1] = PRE ? w1pre[b] : ld_table(&tw[k * TSTEP]);
 #pragma unroll
             for (int r = 2; r < R; ++r) {
                 const int hi = (r >= 8) ? 8 : (r >= 4 ? 4 : 2);   // largest power of two <= r
@@ -231,20 +233,35 @@ __host__ __device__ constexpr int fft_num_passes(int n2, int e)
 // (pass p writes bufs[p & 1]); `sync` is the barrier among the participating threads and
 // `after_first` runs once right after the first barrier (used to refill the hop ring).
 // On return v[m] = Z[t + m*NT]; the exchange buffer NOT read last is bufs[(passes - 1) & 1].
-template <int N2, int E, int NS, int PASS, class Sync, class Hook>
+// PF: the next pass's twiddle load is issued before the barrier in front of it (two registers across the
+// barrier; the register-capped batch kernels do without)
+template <int N2, int E, int NS, int PASS, bool PF = false, class Sync, class Hook>
 __device__ __forceinline__ void fft_run(float2 (&v)[E], int t, float2 *buf0, float2 *buf1,
-                                        const float2 *__restrict__ tw, Sync sync, Hook after_first)
+                                        const float2 *__restrict__ tw, Sync sync, Hook after_first,
+                                        const float2 *w1cur = nullptr)
 {
+    constexpr int NT = N2 / E;
     constexpr int REM = N2 / NS;
     constexpr int R = REM < E ? REM : E;
     constexpr bool LAST = (NS * R == N2);
+    constexpr bool PRE = PF && PASS > 0;
     float2 *ex = (PASS & 1) ? buf1 : buf0;
-    fft_pass<N2, E, R, NS, LAST>(v, t, ex, tw);
+    fft_pass<N2, E, R, NS, LAST, 1, PRE>(v, t, ex, tw, w1cur);
     if constexpr (!LAST) {
+        constexpr int NSn = NS * R;                       // geometry of the next pass
+        constexpr int REMn = N2 / NSn;
+        constexpr int Rn = REMn < E ? REMn : E;
+        constexpr int BPTn = E / Rn;
+        constexpr int TSTEPn = N2 / (NSn * Rn);
+        float2 w1n[BPTn];
+        if constexpr (PF) {
+#pragma unroll
+            for (int b = 0; b < BPTn; ++b) w1n[b] = ld_table(&tw[((t + b * NT) & (NSn - 1)) * TSTEPn]);
+        }
         sync();
         if constexpr (PASS == 0) after_first();
         fft_reload<N2, E>(v, t, ex);
-        fft_run<N2, E, NS * R, PASS + 1>(v, t, buf0, buf1, tw, sync, after_first);
+        fft_run<N2, E, NSn, PASS + 1, PF>(v, t, buf0, buf1, tw, sync, after_first, w1n);
     }
 }
 
