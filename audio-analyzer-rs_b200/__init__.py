@@ -54,6 +54,7 @@ from ._ffi import (  # noqa: F401
     notes_from_stable,
     notes_from_stable_device,
     num_frames,
+    plan_segments,
     pinned_empty,
     set_device,
     synth_clips_device,

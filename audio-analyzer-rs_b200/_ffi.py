@@ -169,6 +169,7 @@ def lib():
         "aa_analyzer_create": (i32, [C.POINTER(Config), pvp]),
         "aa_analyzer_destroy": (i32, [vp]),
         "aa_num_frames": (i64, [C.POINTER(Config), i64]),
+        "aa_plan_segments": (i32, [i64, i64, i32, vp]),
         "aa_analyze_device": (i32, [vp, vp, i64, i64, i64, vp, C.POINTER(_Outputs), vp]),
         "aa_analyze_host": (i32, [vp, vp, i64, i64, i64, vp, C.POINTER(_Outputs)]),
         "aa_analyzer_last_launches": (i64, [vp]),
@@ -234,6 +235,13 @@ def set_device(i: int):
 
 def num_frames(cfg: Config, clip_len: int) -> int:
     return int(lib().aa_num_frames(C.byref(cfg), clip_len))
+
+
+def plan_segments(T: int, n_clips: int, resident_ctas: int) -> list[int]:
+    """Frame boundaries of the time segments the batch path cuts every clip into (aa_plan_segments)."""
+    starts = (C.c_int32 * 9)()
+    n = int(lib().aa_plan_segments(T, n_clips, resident_ctas, starts))
+    return [int(starts[i]) for i in range(n + 1)]
 
 
 def _ptr(a):

@@ -495,6 +495,17 @@ static int plan_segments(int64_t T, int64_t n_clips, int grid, int *start)
     return n;
 }
 
+extern "C" AA_API int aa_plan_segments(int64_t T, int64_t n_clips, int resident_ctas, int32_t *starts)
+{
+    static_assert(AA_MAX_SEGMENTS == aa::AA_MAX_SEG, "header and kernel disagree on the segment limit");
+    int tmp[aa::AA_MAX_SEG + 1];
+    if (T < 0) T = 0;
+    const int n = plan_segments(T, n_clips, resident_ctas, tmp);
+    if (starts)
+        for (int i = 0; i <= n; ++i) starts[i] = tmp[i];
+    return n;
+}
+
 static aa_status analyze_device_impl(aa_analyzer *h, const float *clips_dev, int64_t n_clips, int64_t clip_len,
                                      int64_t clip_stride, const uint8_t *onset_in_dev, const aa_outputs *out,
                                      float *state, cudaStream_t s, int64_t *launches)

@@ -166,6 +166,13 @@ AA_API aa_status aa_analyzer_destroy(aa_analyzer *h);
 /* T = (clip_len - n)/hop + 1, 0 if clip_len < n: frame t covers samples [t*hop, t*hop+n),
  * the offline reading of `while available_samples >= window_size` (stft.rs:273,436). */
 AA_API int64_t   aa_num_frames(const aa_config *cfg, int64_t clip_len);
+/* How aa_analyze_* cuts the T frames of every clip into time segments when n_clips clips are dealt to
+ * `resident_ctas` persistent CTAs (NEW, no reference: the reference analyses one stream).  A segment hands the
+ * analyzer state (what stft.rs:209-211, onset.rs:149-200 and PitchTracker keep between frames) to the next one
+ * through HBM, so results do not depend on the plan.  Writes starts[0..n] (starts[0] = 0, starts[n] = T, at
+ * most AA_MAX_SEGMENTS + 1 entries) and returns n >= 1; n == 1 means whole clips.  Pure host arithmetic. */
+#define AA_MAX_SEGMENTS 8
+AA_API int       aa_plan_segments(int64_t T, int64_t n_clips, int resident_ctas, int32_t *starts);
 
 /* clips_dev: n_clips clips, clip c starting at clips_dev + c*clip_stride (samples,
  * multiple of 4; clips may overlap, which is how hop-aligned chunks of a long stream

@@ -39,6 +39,26 @@ def test_num_frames(aa):
     assert aa.num_frames(aa.Config(n=4096, sample_rate=48000.0), 1440000) == 1403
 
 
+def test_segment_plan_invariants(aa):
+    """aa_plan_segments (pure host arithmetic): the time segments of the batch path tile [0, T) with at least one
+    frame each, get shorter towards the end, and fall back to whole clips where cutting cannot help."""
+    assert aa.plan_segments(1403, 1024, 444) == [0, 701, 1052, 1227, 1315, 1359, 1403]
+    for T in (1, 2, 63, 64, 65, 128, 129, 858, 1403, 10 ** 6, 2 ** 31 - 1):
+        for n_clips, ctas in ((445, 444), (1024, 444), (5000, 740), (7103, 444)):
+            s = aa.plan_segments(T, n_clips, ctas)
+            assert s[0] == 0 and s[-1] == T and 2 <= len(s) <= 9
+            lens = [b - a for a, b in zip(s, s[1:])]
+            assert all(x >= 1 for x in lens)
+            assert all(a >= b - 1 for a, b in zip(lens, lens[1:-1] + lens[-1:])) or len(lens) <= 2   # non-increasing (± rounding)
+            if T <= 64:
+                assert len(s) == 2                          # too short to cut
+    # at most one clip per resident CTA, or so many clips that the ragged end is negligible: whole clips
+    assert aa.plan_segments(1403, 444, 444) == [0, 1403]
+    assert aa.plan_segments(1403, 100, 444) == [0, 1403]
+    assert aa.plan_segments(858, 65536, 740) == [0, 858]
+    assert aa.plan_segments(0, 1024, 444) == [0, 0]
+
+
 def test_default_configs_are_the_reference_constants(aa):
     cfg = aa.Config()
     aa.lib().aa_config_default_pitch(C.byref(cfg), 44100.0)
