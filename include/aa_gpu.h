@@ -178,7 +178,9 @@ AA_API int       aa_plan_segments(int64_t T, int64_t n_clips, int resident_ctas,
  * multiple of 4; clips may overlap, which is how hop-aligned chunks of a long stream
  * with a window halo are expressed).  Analyzer state (floors, trackers) starts fresh
  * for every clip.  onset_in_dev (optional, [n_clips*T] bytes) is PitchTracker's
- * `onset` argument per frame (the reference's onset_pending flag, stft.rs:387). */
+ * `onset` argument per frame (the reference's onset_pending flag, stft.rs:387).
+ * A handle owns the work queue and the segment hand-off buffers of its launches: calls on one handle
+ * must not overlap on the device (one stream per handle, or several handles). */
 AA_API aa_status aa_analyze_device(aa_analyzer *h, const float *clips_dev, int64_t n_clips,
                                    int64_t clip_len, int64_t clip_stride,
                                    const uint8_t *onset_in_dev, const aa_outputs *out_dev,
