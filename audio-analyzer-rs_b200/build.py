@@ -42,10 +42,12 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     nvcc = _nvcc()
     extra = []
     for macro in sorted(os.environ):          # tuning knobs for experiments: env var AA_* -> -D
-        if macro.startswith("AA_") and os.environ[macro] != "":
+        if macro.startswith("AA_") and macro != "AA_SO_OUT" and os.environ[macro] != "":
             extra.append(f"-D{macro}={os.environ[macro]}")
             force = True
-    objdir = os.path.join(HERE, "build")
+    # AA_SO_OUT=path: build an experiment variant next to the in-tree library without touching it
+    so_out = os.environ.get("AA_SO_OUT") or SO
+    objdir = os.path.join(HERE, "build") if so_out == SO else os.path.join(HERE, "build", "variant")
     os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     objs = []
@@ -69,12 +71,12 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
             sys.stdout.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    if force or procs or _stale(SO, objs):
-        cmd = [nvcc, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    if force or procs or _stale(so_out, objs):
+        cmd = [nvcc, "-shared", "-o", so_out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
-    return SO
+    return so_out
 
 
 if __name__ == "__main__":
