@@ -369,6 +369,21 @@ def test_time_segments_equal_whole_clips(aa, O, torch_cuda):
         assert (iso["features"]["n_pitches"] == h_feat["n_pitches"]).mean() > 0.97
 
 
+def test_whole_clip_queue_path(torch_cuda):
+    """Batches of 16 or more clips per resident CTA (and AA_SEG_MIN=0) deal whole clips from the device-wide queue.
+    The segment planner reads AA_SEG_MIN once per process, so the comparison of the queue path with the static
+    path runs in a child process with segmentation switched off."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AA_SEG_MIN="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "-m", "gpu",
+                        "tests/test_gpu_analyze.py::test_time_segments_equal_whole_clips"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_note_records_match_reference_from_freq(aa, O, torch_cuda):
     """NEXT row f2: Note::from_freq (theory.rs:195-209) on the device for every stable pitch."""
     x = np.stack([signals.sine(440.0, 44100.0, 30000), signals.multitone(3, 44100.0, 30000)])
