@@ -41,12 +41,16 @@ def _stale(target: str, deps: list[str]) -> bool:
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
     nvcc = _nvcc()
     extra = []
-    for macro in sorted(os.environ):          # tuning knobs for experiments: env var AA_* -> -D
-        if macro.startswith("AA_") and macro != "AA_SO_OUT" and os.environ[macro] != "":
-            extra.append(f"-D{macro}={os.environ[macro]}")
-            force = True
-    # AA_SO_OUT=path: build an experiment variant next to the in-tree library without touching it
+    # AA_SO_OUT=path: build an experiment variant next to the in-tree library without touching it.
+    # Compile-time experiment knobs (env AA_DEF_<NAME>=v -> -DAA_<NAME>=v) are honoured ONLY for such a
+    # variant: the in-tree library is always built from the sources alone, so a leftover environment
+    # variable (or a run-time knob like AA_SEG_MIN) can never change the shipped kernel.
     so_out = os.environ.get("AA_SO_OUT") or SO
+    if so_out != SO:
+        for macro in sorted(os.environ):
+            if macro.startswith("AA_DEF_") and os.environ[macro] != "":
+                extra.append(f"-DAA_{macro[len('AA_DEF_'):]}={os.environ[macro]}")
+                force = True
     objdir = os.path.join(HERE, "build") if so_out == SO else os.path.join(HERE, "build", "variant")
     os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]

@@ -20,7 +20,7 @@ using namespace aa;
 // errors
 // ---------------------------------------------------------------------------
 static thread_local std::string g_err;
-static int g_device = 0;
+static thread_local int g_device = 0;   // aa_set_device is per calling thread (distinct handles on distinct threads)
 
 static aa_status fail(aa_status code, const std::string &msg)
 {
@@ -52,7 +52,7 @@ static aa_status check_device(int *num_sms)
     if (g_device >= count) return fail(AA_ERR_NO_DEVICE, "selected device index out of range");
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, g_device));
-    if (prop.major != 10)
+    if (prop.major != 10 || prop.minor != 0)   // sm_100a cubins only: no PTX, nothing runs on 10.3
         return fail(AA_ERR_NO_DEVICE, std::string("device '") + prop.name +
                                           "' is not sm_100; libaa_gpu is built for sm_100a only");
     CU(cudaSetDevice(g_device));
@@ -583,7 +583,30 @@ extern "C" AA_API aa_status aa_analyze_device(aa_analyzer *h, const float *clips
 
 // format / channels: what the host buffer holds (AA_PCM_*, interleaved); mono f32 is copied straight into the
 // analysis input, anything else goes through the ingest kernel (mod.rs:765-792) on the device
+static aa_status analyze_host_body(aa_analyzer *h, const void *clips_host, int format, int channels, int64_t n_clips,
+                                   int64_t clip_len, int64_t clip_stride, const uint8_t *onset_in_host,
+                                   const aa_outputs *out_host);
+
+// On any failure the copies of earlier clip groups may still be in flight to / from the caller's host buffers:
+// drain the three streams before the error is returned, so the caller may free or reuse its buffers.
 static aa_status analyze_host_impl(aa_analyzer *h, const void *clips_host, int format, int channels, int64_t n_clips,
+                                   int64_t clip_len, int64_t clip_stride, const uint8_t *onset_in_host,
+                                   const aa_outputs *out_host)
+{
+    const aa_status st = analyze_host_body(h, clips_host, format, channels, n_clips, clip_len, clip_stride,
+                                           onset_in_host, out_host);
+    if (st != AA_OK && h) {
+        const std::string keep = g_err;
+        cudaStreamSynchronize(h->s_h2d);
+        cudaStreamSynchronize(h->s_compute);
+        cudaStreamSynchronize(h->s_d2h);
+        cudaGetLastError();
+        g_err = keep;
+    }
+    return st;
+}
+
+static aa_status analyze_host_body(aa_analyzer *h, const void *clips_host, int format, int channels, int64_t n_clips,
                                    int64_t clip_len, int64_t clip_stride, const uint8_t *onset_in_host,
                                    const aa_outputs *out_host)
 {
@@ -857,6 +880,18 @@ extern "C" AA_API aa_status aa_stream_push(aa_stream *h, const float *samples, i
     const int64_t ring = h->cap / 8;
     if (count > ring) return fail(AA_ERR_OVERFLOW, "aa_stream_push: more samples than the ring holds in one push");
     CU(cudaSetDevice(h->an->device));
+    // Validate before anything is mutated: a push that fails consumed nothing, so the caller may poll
+    // and retry the same samples (the frames this push completes must fit the result ring).
+    {
+        const int64_t avail = h->wr - h->rd + count;
+        int64_t T = avail >= h->n ? (avail - h->n) / h->hop + 1 : 0;
+        if (T > h->max_frames_per_push) T = h->max_frames_per_push;
+        if (h->out_count + T > h->out_cap)
+            return fail(AA_ERR_OVERFLOW, "aa_stream_push: result ring full, call aa_stream_poll (nothing was consumed)");
+        const int64_t lead = h->rd - (h->rd & ~(int64_t)3);
+        if (h->wr + count > h->cap && lead + avail > h->cap)
+            return fail(AA_ERR_OVERFLOW, "aa_stream_push: sample ring full (nothing was consumed)");
+    }
     // previous push fully drained (results already in the host ring) before staging is reused
     CU(cudaStreamSynchronize(h->s));
 
@@ -881,8 +916,6 @@ extern "C" AA_API aa_status aa_stream_push(aa_stream *h, const float *samples, i
     if (avail < h->n) return AA_OK;
     int64_t T = (avail - h->n) / h->hop + 1;
     if (T > h->max_frames_per_push) T = h->max_frames_per_push;
-    if (h->out_count + T > h->out_cap)
-        return fail(AA_ERR_OVERFLOW, "aa_stream_push: result ring full, call aa_stream_poll");
     if (h->rd & 3) return fail(AA_ERR_INVALID, "aa_stream: hop must keep the read position 16-byte aligned");
 
     // onset_pending (stft.rs:387) reaches the tracker as a per-frame flag array; without a pending onset the

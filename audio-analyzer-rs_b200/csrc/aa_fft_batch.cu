@@ -5,6 +5,7 @@
 // One CTA transforms one frame at a time (grid-stride over the batch): coalesced float2
 // loads straight into the register-resident Stockham FFT of aa_fft.cuh, the realfft
 // split post-pass, coalesced float2 stores of the n/2+1 bins.
+#include <atomic>
 #include "aa_fft.cuh"
 #include "aa_internal.h"
 #include "aa_tma.cuh"
@@ -172,14 +173,14 @@ static cudaError_t launch_fwd(const Tables &tab, const float *in, int64_t batch,
     int64_t grid = (int64_t)num_sms * per_sm;
     if (grid > batch) grid = batch;
     using FL = FwdLayout<N>;
-    static unsigned long long configured = 0ull;     // the opt-in shared-memory size is a per-device attribute
+    static std::atomic<unsigned long long> configured{0ull};     // the opt-in shared-memory size is a per-device attribute
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (FL::total > 48 * 1024 && (dev >= 64 || !((configured >> dev) & 1ull))) {
+    if (FL::total > 48 * 1024 && (dev >= 64 || !((configured.load(std::memory_order_acquire) >> dev) & 1ull))) {
         e = cudaFuncSetAttribute(fft_forward_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FL::total);
         if (e != cudaSuccess) return e;
-        if (dev < 64) configured |= 1ull << dev;
+        if (dev < 64) configured.fetch_or(1ull << dev, std::memory_order_release);
     }
     fft_forward_kernel<N><<<(unsigned)grid, NT, FL::total, s>>>(in, batch, out, tab);
     return cudaGetLastError();

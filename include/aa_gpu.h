@@ -48,7 +48,7 @@ typedef int32_t aa_status;
 AA_API const char *aa_last_error(void);
 AA_API int32_t     aa_version(void);                     /* 10000*major + 100*minor + patch */
 AA_API aa_status   aa_device_count(int32_t *count);
-AA_API aa_status   aa_set_device(int32_t device);        /* device used by subsequently created handles */
+AA_API aa_status   aa_set_device(int32_t device);        /* device used by handles the CALLING THREAD creates afterwards (thread-local) */
 
 /* pinned host memory for the *_host entry points (pageable memory also works, slower) */
 AA_API aa_status aa_host_alloc(size_t bytes, void **out);

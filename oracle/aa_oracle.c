@@ -323,6 +323,10 @@ void aao_pitch_floor_update(aao_pitch_floor *s, const float *mags, float global_
         effective_floor[k] = fminf(s->nf[k], global_floor * 2.5f);
 }
 
+/* parity-test taps: the raw recurrent state after the update of the current frame */
+const float *aao_pitch_floor_nf(const aao_pitch_floor *s) { return s->nf; }
+const float *aao_pitch_floor_vol(const aao_pitch_floor *s) { return s->vol; }
+
 /* ------------------------------------------------------------------------- */
 /* a7: STFT::extract_pitches, stft.rs:443-620                                  */
 /* ------------------------------------------------------------------------- */
@@ -344,19 +348,53 @@ static inline void margin_update2(float *m, int *src, float dist, int tag)
 
 typedef struct { int bin; float score; } aao_cand;
 
+/* Magnitude-perturbation margin (aao_pitch_diag.cand_eps): for a decision lhs > rhs taken on quantities
+ * derived from the frame's magnitudes, the smallest uniform |dm| (every magnitude, and every floor value
+ * that is not clamped to its constant, moved by at most dm in the worst direction) that could flip it is
+ * |lhs - rhs| / (L1 norm of the gradient of lhs - rhs with respect to those values), first order. */
+static inline void cand_update(float *m, int *src, float gap, float sens, int tag)
+{
+    if (!(sens > 0.0f)) return;
+    if (gap < 0.0f) gap = -gap;
+    float e = gap / sens;
+    if (e < *m) { *m = e; *src = tag; }
+}
+
+static int extract_pitches_impl(const float *magnitudes, int half_size, float bin_width,
+                                float min_freq, float max_freq, const float *noise_floor,
+                                const float *floor_sens, float *out_pairs, uint8_t *peak_mask,
+                                aao_pitch_diag *diag);
+
 int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
                         float min_freq, float max_freq, const float *noise_floor,
                         float *out_pairs, uint8_t *peak_mask, aao_pitch_diag *diag)
 {
+    return extract_pitches_impl(magnitudes, half_size, bin_width, min_freq, max_freq, noise_floor, NULL,
+                                out_pairs, peak_mask, diag);
+}
+
+/* floor_sens[k] (optional): d noise_floor[k] / d magnitude bound -- 0 where the effective floor sits at its
+ * clamp 2.5 * global_floor (stft.rs:366), 1 where it is the adaptive floor (an EMA of past magnitudes);
+ * NULL = 1 everywhere. */
+static int extract_pitches_impl(const float *magnitudes, int half_size, float bin_width,
+                                float min_freq, float max_freq, const float *noise_floor,
+                                const float *floor_sens, float *out_pairs, uint8_t *peak_mask,
+                                aao_pitch_diag *diag)
+{
     enum { MAX_HARMONICS = 14, MAX_NOTES = 8 };                     /* :451-452 */
     float margin = 1.0f;
     int margin_src = 0;
+    float ceps = 1e30f;           /* cand_eps, see cand_update */
+    int ceps_src = 0;
     (void)g_margin_src_dummy;
     if (diag) {
         memset(diag, 0, sizeof(*diag));
         diag->min_margin = 1.0f;
+        diag->cand_eps = 1e30f;
         for (int i = 0; i < MAX_NOTES; ++i) diag->out_bins[i] = -1;
     }
+#define FSENS(k) (floor_sens ? floor_sens[(k)] : 1.0f)
+#define CEPS(gap, sens, tag) cand_update(&ceps, &ceps_src, (gap), (sens), (tag))
     if (peak_mask) memset(peak_mask, 0, (size_t)half_size);
 
     size_t min_bin = f32_as_usize(ceilf(min_freq / bin_width));      /* :454 */
@@ -382,10 +420,13 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
 
     float *scores = (float *)calloc((size_t)half_size, sizeof(float));    /* :475 */
     float *frac_bins = (float *)calloc((size_t)half_size, sizeof(float)); /* :476 */
+    float *sens_frac = (float *)calloc((size_t)half_size, sizeof(float));  /* |d frac_bin / d mags|_1 */
+    float *sens_score = (float *)calloc((size_t)half_size, sizeof(float)); /* |d score / d mags|_1    */
     int n_scored = 0;
     for (int pi = 0; pi < n_peaks; ++pi) {                           /* :477 */
         int k = peak_bins[pi];
         float fund_mag = magnitudes[k];
+        CEPS(fund_mag - noise_floor[k] * 5.0f, 1.0f + 5.0f * FSENS(k), 104);
         if (fund_mag < noise_floor[k] * 5.0f) {                      /* :479-482 */
             scores[k] = 0.0f;
             continue;
@@ -393,6 +434,7 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
         ++n_scored;
         float frac_bin;
         int frac_is_exact = 0;
+        float sfrac = 0.0f;
         if (k >= 1 && k + 1 < half_size) {                           /* :484-494 */
             float y_l = logf(magnitudes[k - 1]);
             float y_c = logf(magnitudes[k]);
@@ -407,18 +449,29 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
                  * every implementation and the comb-window boundaries carry no rounding risk */
                 frac_is_exact = fabsf(raw) > 1.001f;
                 if (!frac_is_exact) margin_update(&margin, fabsf(raw) - 1.0f, 11);
+                {   /* d raw / d (m_l, m_c, m_r) through y = ln m */
+                    float a = y_l - y_r, d2 = denom * denom;
+                    float gl = fabsf(0.5f * (1.0f / denom - a / d2)) / magnitudes[k - 1];
+                    float gc = fabsf(a / d2) / magnitudes[k];
+                    float gr = fabsf(0.5f * (-1.0f / denom - a / d2)) / magnitudes[k + 1];
+                    float sraw = gl + gc + gr;
+                    CEPS(fabsf(raw) - 1.0f, sraw, 111);       /* the clamp itself (:492) */
+                    sfrac = fabsf(raw) > 1.0f ? 0.0f : sraw;  /* a clamped delta is an exact +-1 */
+                }
             }
             frac_bin = (float)k + delta;
         } else {
             frac_bin = (float)k;
         }
         frac_bins[k] = frac_bin;                                     /* :498 */
+        sens_frac[k] = sfrac;
         float score = fund_mag;
         size_t last = (size_t)k;
         int longest_run = 0, current_run = 0, total_harms = 0;
         for (int n = 2; n <= MAX_HARMONICS; ++n) {                   /* :504 */
             float expected_f = frac_bin * (float)n;                  /* :505 */
             if (!frac_is_exact) margin_update(&margin, (expected_f - (float)half_size) / (float)n, 1);
+            CEPS(expected_f - (float)half_size, (float)n * sfrac, 112);
             if (expected_f >= (float)half_size) break;               /* :506-508 */
             if (!frac_is_exact) {   /* distance of expected_f from the nearest integer, relative */
                 float r = expected_f - floorf(expected_f);
@@ -430,14 +483,37 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
             size_t search_end = f32_as_usize(ceilf(expected_f + 1.0f));      /* :510 */
             if (search_end > (size_t)half_size - 1) search_end = (size_t)half_size - 1;
 
+            if (sfrac > 0.0f) {
+                /* window boundaries: floor(e - 1) moves when e - 1 crosses an integer (one bin enters or
+                 * leaves at the low end), ceil(e + 1) likewise at the high end; that matters only if the bin
+                 * concerned is a peak the search could take */
+                float lo = expected_f - 1.0f, hi = expected_f + 1.0f;
+                float fl = floorf(lo), ce = ceilf(hi);
+                long ifl = (long)fl, ice = (long)ce;
+                float ns = (float)n * sfrac;
+                if (ifl - 1 > (long)last && ifl - 1 >= 0 && ifl - 1 < half_size && is_peak[ifl - 1])
+                    CEPS(lo - fl, ns, 113);                      /* bin fl-1 would enter */
+                if (ifl > (long)last && ifl >= 0 && ifl < half_size && is_peak[ifl])
+                    CEPS(fl + 1.0f - lo, ns, 113);               /* bin fl would leave   */
+                if (ice > (long)last && ice >= 0 && ice <= half_size - 1 && is_peak[ice])
+                    CEPS(hi - (ce - 1.0f), ns, 114);             /* bin ce would leave   */
+                if (ice + 1 > (long)last && ice + 1 <= half_size - 1 && is_peak[ice + 1])
+                    CEPS(ce - hi, ns, 114);                      /* bin ce+1 would enter */
+            }
             size_t best_hbin = 0;                                    /* :512-520 */
-            float best_mag = 0.0f;
+            float best_mag = 0.0f, second_mag = -1.0f;
             for (size_t h = search_start; h <= search_end; ++h) {
-                if (is_peak[h] && magnitudes[h] > best_mag) {
-                    best_mag = magnitudes[h];
-                    best_hbin = h;
+                if (is_peak[h]) {
+                    if (magnitudes[h] > best_mag) {
+                        second_mag = best_mag;
+                        best_mag = magnitudes[h];
+                        best_hbin = h;
+                    } else if (magnitudes[h] > second_mag) {
+                        second_mag = magnitudes[h];
+                    }
                 }
             }
+            if (best_hbin != 0 && second_mag > 0.0f) CEPS(best_mag - second_mag, 2.0f, 115);   /* :516 */
             if (best_hbin != 0) {                                    /* :521-531 */
                 score += best_mag;
                 last = best_hbin;
@@ -449,6 +525,7 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
             }
         }
         if (current_run > longest_run) longest_run = current_run;    /* :533-535 */
+        if (longest_run < 3) CEPS(fund_mag - 15.0f * noise_floor[k], 1.0f + 15.0f * FSENS(k), 116);
         if (longest_run < 3 && fund_mag < 15.0f * noise_floor[k]) {  /* :536-537 */
             scores[k] = 0.0f;
         } else {                                                     /* :539-543 */
@@ -457,6 +534,8 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
             float struct_mult = (STRUCT_BASE + (float)longest_run + (float)total_harms / 2.0f)
                                 / (STRUCT_BASE + (float)MAX_HARMONICS);
             scores[k] = log_score * struct_mult;
+            /* score = log2(0.5 + sum of 1 + total_harms magnitudes) * struct_mult */
+            sens_score[k] = (float)(1 + total_harms) * fabsf(struct_mult) / ((0.5f + score) * 0.69314718f);
         }
     }
     if (diag) diag->n_scored = n_scored;
@@ -467,6 +546,12 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
         if (s > max_score) max_score = s;          /* f32::max fold from 0.0 */
     }
     int n_out = 0;
+    float sens_max = 0.0f;
+    for (int pi = 0; pi < n_peaks; ++pi) {
+        int k = peak_bins[pi];
+        if (scores[k] != 0.0f) CEPS(scores[k], sens_score[k], 117);  /* sign of a score against the fold's 0.0 */
+        if (scores[k] == max_score && sens_score[k] > sens_max) sens_max = sens_score[k];
+    }
     if (max_score == 0.0f) goto done;                                /* :548-550 */
     {
         float cutoff = max_score * 0.5f;                             /* :551 */
@@ -475,6 +560,8 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
         for (int pi = 0; pi < n_peaks; ++pi) {                       /* :553-562 */
             int k = peak_bins[pi];
             if (scores[k] != 0.0f) margin_update(&margin, (scores[k] - cutoff) / cutoff, 3);
+            if (scores[k] != 0.0f && scores[k] != max_score)
+                CEPS(scores[k] - cutoff, sens_score[k] + 0.5f * sens_max, 118);
             if (scores[k] >= cutoff) { cand[nc].bin = k; cand[nc].score = scores[k]; ++nc; }
         }
         if (diag) diag->n_candidates = nc;
@@ -492,20 +579,26 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
                 {   /* margins: ratio near x.5, |ratio/nearest-1| near 0.03, score test */
                     float fr = ratio - floorf(ratio);
                     if (ratio > 1.4f && ratio < 5.6f) {
+                        float fbi = frac_bins[cand[i].bin], fbj = frac_bins[cand[j].bin];
+                        float sr_ = sens_frac[cand[i].bin] / fbj + fbi * sens_frac[cand[j].bin] / (fbj * fbj);
                         margin_update(&margin, fr - 0.5f, 4);
+                        CEPS(fr - 0.5f, sr_, 119);
                         if (nearest >= 2.0f && nearest <= 5.0f) {
                             float dev = fabsf(ratio / nearest - 1.0f);
                             margin_update(&margin, (dev - 0.03f) / 0.03f, 5);
-                            if (dev < 0.03f)
+                            CEPS(dev - 0.03f, sr_ / nearest, 120);
+                            if (dev < 0.03f) {
                                 margin_update(&margin, (score_i - score_j * 1.05f) / score_i, 6);
+                                CEPS(score_i - score_j * 1.05f,
+                                     sens_score[cand[i].bin] + 1.05f * sens_score[cand[j].bin], 121);
+                            }
                         }
                     }
                 }
                 if (nearest >= 2.0f && nearest <= 5.0f
                     && fabsf(ratio / nearest - 1.0f) < 0.03f
                     && score_i < score_j * 1.05f) {
-                    suppressed[i] = 1;
-                    break;                         /* `any` short-circuits */
+                    suppressed[i] = 1;             /* `any` short-circuits; the loop goes on for the margins only */
                 }
             }
         }
@@ -523,8 +616,10 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
             while (j >= 0 && cand[j].score < c.score) { cand[j + 1] = cand[j]; --j; }
             cand[j + 1] = c;
         }
-        for (int i = 1; i < nk; ++i)
+        for (int i = 1; i < nk; ++i) {
             margin_update(&margin, (cand[i - 1].score - cand[i].score) / cand[i - 1].score, 7);
+            CEPS(cand[i - 1].score - cand[i].score, sens_score[cand[i - 1].bin] + sens_score[cand[i].bin], 122);
+        }
 
         const float MIN_BIN_SEPARATION = 2.0f;                       /* :594-605 */
         int nd = 0;
@@ -534,6 +629,7 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
             for (int j = 0; j < nd; ++j) {
                 float d = fabsf(frac_i - frac_bins[cand[j].bin]);
                 margin_update(&margin, (d - MIN_BIN_SEPARATION) / MIN_BIN_SEPARATION, 8);
+                CEPS(d - MIN_BIN_SEPARATION, sens_frac[cand[i].bin] + sens_frac[cand[j].bin], 123);
                 if (d < MIN_BIN_SEPARATION) { conflict = 1; break; }
             }
             if (!conflict) cand[nd++] = cand[i];
@@ -544,6 +640,8 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
             float freq = frac_bins[cand[i].bin] * bin_width;
             margin_update(&margin, (freq - min_freq) / min_freq, 9);
             margin_update(&margin, (freq - max_freq) / max_freq, 10);
+            CEPS(freq - min_freq, bin_width * sens_frac[cand[i].bin], 124);
+            CEPS(freq - max_freq, bin_width * sens_frac[cand[i].bin], 124);
             if (freq >= min_freq && freq <= max_freq) {
                 out_pairs[2 * n_out] = freq;
                 out_pairs[2 * n_out + 1] = cand[i].score;
@@ -554,9 +652,14 @@ int aao_extract_pitches(const float *magnitudes, int half_size, float bin_width,
         free(cand);
     }
 done:
-    if (diag) { diag->n_out = n_out; diag->min_margin = margin; diag->margin_src = margin_src; }
-    free(is_peak); free(peak_bins); free(scores); free(frac_bins);
+    if (diag) {
+        diag->n_out = n_out; diag->min_margin = margin; diag->margin_src = margin_src;
+        diag->cand_eps = ceps; diag->cand_src = ceps_src;
+    }
+    free(is_peak); free(peak_bins); free(scores); free(frac_bins); free(sens_frac); free(sens_score);
     return n_out;
+#undef FSENS
+#undef CEPS
 }
 
 /* ------------------------------------------------------------------------- */
@@ -671,6 +774,8 @@ void aao_onset_destroy(aao_onset *s)
     if (!s) return;
     free(s->prev_magnitude); free(s->noise_floor_per_bin); free(s);
 }
+
+const float *aao_onset_floor(const aao_onset *s) { return s->noise_floor_per_bin; }
 
 void aao_onset_reset(aao_onset *s)
 {
@@ -844,15 +949,35 @@ int64_t aao_analyze_clip(const aao_config *cfg, const float *samples, int64_t le
                          aao_features *feat_out, aao_stable *stable_out,
                          aao_pitch_diag *diag_out)
 {
+    aao_taps taps;
+    memset(&taps, 0, sizeof(taps));
+    taps.mags = mags_out;
+    taps.floor = floor_out;
+    taps.peak_mask = peak_mask_out;
+    taps.features = feat_out;
+    taps.stable = stable_out;
+    taps.diag = diag_out;
+    return aao_analyze_clip_ex(cfg, samples, len, mags_in, onset_in, &taps);
+}
+
+int64_t aao_analyze_clip_ex(const aao_config *cfg, const float *samples, int64_t len,
+                            const float *mags_in, const uint8_t *onset_in, const aao_taps *taps)
+{
     const int n = cfg->n, hop = cfg->hop, half = n / 2 + 1;
     const int64_t T = aao_num_frames(len, n, hop);
     if (T <= 0) return 0;
+    float *mags_out = taps->mags, *floor_out = taps->floor;
+    uint8_t *peak_mask_out = taps->peak_mask;
+    aao_features *feat_out = taps->features;
+    aao_stable *stable_out = taps->stable;
+    aao_pitch_diag *diag_out = taps->diag;
 
     float *window = (float *)malloc(sizeof(float) * (size_t)n);
     float *td = (float *)malloc(sizeof(float) * (size_t)n);
     float *spec = (float *)malloc(sizeof(float) * 2 * (size_t)half);
     float *mags = (float *)malloc(sizeof(float) * (size_t)half);
     float *eff = (float *)malloc(sizeof(float) * (size_t)half);
+    float *fsens = (float *)malloc(sizeof(float) * (size_t)half);
     aao_hann_window(n, window);                              /* stft.rs:179 */
     aao_fft *fft = mags_in ? NULL : aao_fft_create(n);       /* stft.rs:180 */
     aao_pitch_floor *pf = aao_pitch_floor_create(half);
@@ -877,10 +1002,14 @@ int64_t aao_analyze_clip(const aao_config *cfg, const float *samples, int64_t le
         if (cfg->features & AAO_FEAT_PITCH) {
             aao_pitch_floor_update(pf, mags, global_floor, eff);
             if (floor_out) memcpy(floor_out + t * half, eff, sizeof(float) * (size_t)half);
+            if (taps->pitch_nf) memcpy(taps->pitch_nf + t * half, aao_pitch_floor_nf(pf), sizeof(float) * (size_t)half);
+            if (taps->pitch_vol) memcpy(taps->pitch_vol + t * half, aao_pitch_floor_vol(pf), sizeof(float) * (size_t)half);
+            /* where the effective floor sits at its clamp it does not move with the magnitudes */
+            for (int k = 0; k < half; ++k) fsens[k] = aao_pitch_floor_nf(pf)[k] > global_floor * 2.5f ? 0.0f : 1.0f;
             float pairs[2 * AAO_MAX_NOTES];
-            int np = aao_extract_pitches(mags, half, bin_width, cfg->min_freq, cfg->max_freq, eff,
-                                         pairs, peak_mask_out ? peak_mask_out + t * half : NULL,
-                                         diag_out ? diag_out + t : NULL);
+            int np = extract_pitches_impl(mags, half, bin_width, cfg->min_freq, cfg->max_freq, eff, fsens,
+                                          pairs, peak_mask_out ? peak_mask_out + t * half : NULL,
+                                          diag_out ? diag_out + t : NULL);
             f.n_pitches = (uint32_t)np;
             for (int i = 0; i < np; ++i) {
                 f.pitch[i].freq = pairs[2 * i];
@@ -899,7 +1028,10 @@ int64_t aao_analyze_clip(const aao_config *cfg, const float *samples, int64_t le
                 }
             }
         }
-        if (cfg->features & AAO_FEAT_ONSET) aao_onset_frame(on, mags, global_floor, &f);
+        if (cfg->features & AAO_FEAT_ONSET) {
+            aao_onset_frame(on, mags, global_floor, &f);
+            if (taps->onset_nf) memcpy(taps->onset_nf + t * half, aao_onset_floor(on), sizeof(float) * (size_t)half);
+        }
         if (cfg->features & AAO_FEAT_CENTROID) f.centroid = aao_centroid(mags, half, bin_width);
         if (feat_out) feat_out[t] = f;
     }
@@ -908,7 +1040,7 @@ int64_t aao_analyze_clip(const aao_config *cfg, const float *samples, int64_t le
     aao_onset_destroy(on);
     aao_pitch_floor_destroy(pf);
     if (fft) aao_fft_destroy(fft);
-    free(eff); free(mags); free(spec); free(td); free(window);
+    free(fsens); free(eff); free(mags); free(spec); free(td); free(window);
     return T;
 }
 

@@ -93,6 +93,18 @@ typedef struct aao_pitch_diag {
      * identical magnitudes and are not included.  */
     float    min_margin;
     int32_t  margin_src;         /* which decision class produced min_margin (1..10, aa_oracle.c) */
+    /* Magnitude-perturbation margin of the CANDIDATE-level decisions of extract_pitches (everything after
+     * the peak pick): the smallest uniform perturbation |dm| of the frame's magnitudes (absolute, first
+     * order, worst-case signs; adaptive floor values count as magnitudes, clamped ones as constants) that
+     * could flip one of them.  Two FFT implementations differ by some measured |dm| per frame; an
+     * end-to-end pitch-list difference on identical peak masks is a documented near-tie iff cand_eps is
+     * below that.  Classes (cand_src): 104 the 5x-floor gate stft.rs:479, 111 delta clamp :492, 112 comb
+     * stop :506, 113 / 114 comb window low / high boundary :509-510, 115 best_mag :516, 116 the 15x-floor
+     * test :536, 117 score sign :547, 118 cutoff :556, 119-121 ghost test :575-580, 122 sort :592, 123
+     * dedup :600, 124 range :613.  The per-BIN decisions (peak pick :465, pitch-floor branches :351-355,
+     * onset burst / floor onset.rs:318,323) are analysed per bin from the state taps (tests/parity.py).  */
+    float    cand_eps;
+    int32_t  cand_src;
 } aao_pitch_diag;
 
 /* ---- a1: window (stft.rs:641-648 == onset.rs:549-556) ------------------------- */
@@ -178,6 +190,23 @@ int64_t aao_analyze_clip(const aao_config *cfg, const float *samples, int64_t le
                          aao_pitch_diag *diag_out);  /* [T]                  */
 
 int64_t aao_num_frames(int64_t len, int n, int hop);
+
+/* The same frame loop with every tap of the parity tests; all pointers optional.  pitch_nf / pitch_vol /
+ * onset_nf: the raw recurrent per-bin state AFTER the frame's update (noise_floor_per_bin stft.rs:209,
+ * bin_volatility :211, the onset detector's noise_floor_per_bin onset.rs:175), [T][half] each. */
+typedef struct aao_taps {
+    float          *mags;        /* [T][half]            */
+    float          *floor;       /* [T][half] eff. floor */
+    uint8_t        *peak_mask;   /* [T][half]            */
+    aao_features   *features;    /* [T]                  */
+    aao_stable     *stable;      /* [T]                  */
+    aao_pitch_diag *diag;        /* [T]                  */
+    float          *pitch_nf;    /* [T][half]            */
+    float          *pitch_vol;   /* [T][half]            */
+    float          *onset_nf;    /* [T][half]            */
+} aao_taps;
+int64_t aao_analyze_clip_ex(const aao_config *cfg, const float *samples, int64_t len,
+                            const float *mags_in, const uint8_t *onset_in, const aao_taps *taps);
 
 /* Clip-parallel driver for the timed CPU baseline: clips are contiguous,
  * clip_len samples each; n_threads pthreads each take whole clips.  Only

@@ -52,9 +52,17 @@ DIAG_DTYPE = np.dtype(
         ("out_bins", "<i4", (MAX_NOTES,)),
         ("min_margin", "<f4"),
         ("margin_src", "<i4"),
+        ("cand_eps", "<f4"),
+        ("cand_src", "<i4"),
     ]
 )
-assert DIAG_DTYPE.itemsize == 56
+assert DIAG_DTYPE.itemsize == 64
+
+
+class Taps(C.Structure):
+    """aao_taps (aa_oracle.h)."""
+    _fields_ = [(k, C.c_void_p) for k in ("mags", "floor", "peak_mask", "features", "stable", "diag",
+                                          "pitch_nf", "pitch_vol", "onset_nf")]
 
 
 class Config(C.Structure):
@@ -165,6 +173,8 @@ def lib():
     L.aao_num_frames.argtypes = [C.c_int64, C.c_int, C.c_int]
     L.aao_analyze_clip.restype = C.c_int64
     L.aao_analyze_clip.argtypes = [C.POINTER(Config), fp, C.c_int64, fp, u8p, fp, fp, u8p, vp, vp, vp]
+    L.aao_analyze_clip_ex.restype = C.c_int64
+    L.aao_analyze_clip_ex.argtypes = [C.POINTER(Config), fp, C.c_int64, fp, u8p, C.POINTER(Taps)]
     L.aao_analyze_batch.restype = C.c_int64
     L.aao_analyze_batch.argtypes = [C.POINTER(Config), fp, C.c_int64, C.c_int64, C.c_int, fp, vp, vp]
     L.aao_cond_params_init.argtypes = [C.POINTER(CondParams), C.c_float, C.c_int]
@@ -324,8 +334,9 @@ def num_frames(length, n, hop):
 
 
 def analyze_clip(cfg: Config, samples=None, mags_in=None, onset_in=None, want_mags=True,
-                 want_floor=False, want_peaks=False, want_diag=False):
-    """Run the frame loop on one clip.  Returns a dict of numpy arrays."""
+                 want_floor=False, want_peaks=False, want_diag=False, want_state=False):
+    """Run the frame loop on one clip.  Returns a dict of numpy arrays.
+    want_state: also the raw per-bin recurrent state after every frame (pitch_nf, pitch_vol, onset_nf)."""
     half = cfg.n // 2 + 1
     if mags_in is not None:
         mags_in = np.ascontiguousarray(mags_in, np.float32)
@@ -347,10 +358,14 @@ def analyze_clip(cfg: Config, samples=None, mags_in=None, onset_in=None, want_ma
     feat = np.zeros(T, FEATURES_DTYPE)
     stable = np.zeros(T, STABLE_DTYPE)
     diag = np.zeros(T, DIAG_DTYPE) if want_diag else None
-    got = lib().aao_analyze_clip(C.byref(cfg), _fp(samples_arr), length, _fp(mags_in), _u8p(onset_in),
-                                 _fp(mags), _fp(floor), _u8p(peaks), _vp(feat), _vp(stable), _vp(diag))
+    state = {k: (np.zeros((T, half), np.float32) if want_state else None) for k in ("pitch_nf", "pitch_vol", "onset_nf")}
+    taps = Taps()
+    for k, a in dict(mags=mags, floor=floor, peak_mask=peaks, features=feat, stable=stable, diag=diag, **state).items():
+        setattr(taps, k, a.ctypes.data if a is not None else None)
+    got = lib().aao_analyze_clip_ex(C.byref(cfg), _fp(samples_arr), length, _fp(mags_in), _u8p(onset_in),
+                                    C.byref(taps))
     assert got == T
-    out.update(mags=mags, floor=floor, peaks=peaks, features=feat, stable=stable, diag=diag)
+    out.update(mags=mags, floor=floor, peaks=peaks, features=feat, stable=stable, diag=diag, **state)
     return out
 
 

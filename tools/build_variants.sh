@@ -1,6 +1,6 @@
 #!/bin/bash
 # Build experiment variants of libaa_gpu.so next to the in-tree library, here (nvcc cross-compiles without a GPU):
-#   tools/build_variants.sh "winpf:AA_WIN_PREFETCH=1" "noredux:AA_NO_REDUX=1 AA_NO_KFB=1"
+#   tools/build_variants.sh "winpf:AA_DEF_WIN_PREFETCH=1" "noredux:AA_DEF_NO_REDUX=1 AA_DEF_NO_KFB=1"   (AA_DEF_X=v -> -DAA_X=v)
 # Each argument is NAME:ENV...; the result is variants/libaa_gpu_NAME.so, which tools/exp_variants.sh benches on
 # the GPU box after the default build (gpurun ships variants/ with the snapshot; *.so is git-ignored).
 mkdir -p variants

@@ -1,5 +1,5 @@
 #!/bin/bash
-# bench the default build, then every prebuilt variants/libaa_gpu_*.so (built here with AA_* knobs: see build.py,
+# bench the default build, then every prebuilt variants/libaa_gpu_*.so (built here with AA_DEF_* knobs: see build.py,
 # AA_SO_OUT); the full log goes to gpurun_out/variants.log
 mkdir -p gpurun_out
 B="--no-e2e --no-cpu --steps 3 --warmup 3"

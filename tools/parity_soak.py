@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Parity soak: many random clips through the C ABI, every window size, compared stage-isolated with the CPU
 oracle (the same checks as tests/test_gpu_analyze.py: bit-exact floors / peak masks / burst counts / max_excess,
-pitch lists equal except oracle-flagged near-ties) plus the conditioning chain.  Prints one JSON line.
+pitch lists equal except oracle-flagged near-ties), END TO END with every difference explained as a
+magnitude-level near-tie or downstream of one (tests/parity.py: e2e_* columns, e2e_unexplained must be 0), plus
+the conditioning chain.  Prints one JSON line.
 Usage: parity_soak.py [--clips 48] [--seed 1]"""
 import argparse
 import importlib
@@ -15,6 +17,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+import parity  # noqa: E402
 import signals  # noqa: E402
 import util  # noqa: E402
 
@@ -45,13 +48,24 @@ def main():
         prod = an.analyze_host(clips, want_dbg=False)
         case = {"n": n, "sr": sr, "db": db, "clips": a.clips, "frames": int(a.clips * tap["T"]), "floor_mismatch": 0,
                 "peak_mismatch": 0, "burst_mismatch": 0, "maxex_mismatch": 0, "pitch_hard_mismatch": 0, "near_tie_frames": 0,
-                "flag_mismatch": 0, "prod_vs_tap_mismatch": 0, "max_mag_err": 0.0}
+                "flag_mismatch": 0, "prod_vs_tap_mismatch": 0, "max_mag_err": 0.0,
+                # end to end (signal -> oracle vs signal -> GPU), every difference classified by tests/parity.py
+                "e2e_peak_bits_differ": 0, "e2e_burst_bits_differ": 0, "e2e_pitch_lists_differ": 0, "e2e_unexplained": 0,
+                "e2e_floor_taint_starts": 0, "e2e_peak_tie_frac_max": 0.0}
         for k in ("features", "stable", "mags"):
             case["prod_vs_tap_mismatch"] += int(tap[k].tobytes() != prod[k].tobytes())
         cfg = O.make_config(n, n // 4, sr, noise_floor_db=db)
         for c in range(a.clips):
-            iso = O.analyze_clip(cfg, mags_in=tap["mags"][c], want_floor=True, want_peaks=True, want_diag=True)
-            e2e = O.analyze_clip(cfg, clips[c], want_mags=True)
+            kw = dict(want_floor=True, want_peaks=True, want_diag=True, want_state=True)
+            iso = O.analyze_clip(cfg, mags_in=tap["mags"][c], **kw)
+            e2e = O.analyze_clip(cfg, clips[c], want_mags=True, **kw)
+            rep = parity.explain(O, cfg, e2e, iso)
+            case["e2e_peak_bits_differ"] += rep["peak_bits_differ"]
+            case["e2e_burst_bits_differ"] += rep["burst_bits_differ"]
+            case["e2e_pitch_lists_differ"] += rep["pitch_lists_differ"]
+            case["e2e_unexplained"] += rep["unexplained"]
+            case["e2e_floor_taint_starts"] += rep["pitch_floor_taint_starts"] + rep["onset_floor_taint_starts"]
+            case["e2e_peak_tie_frac_max"] = max(case["e2e_peak_tie_frac_max"], rep["peak_tie_frac"])
             case["max_mag_err"] = max(case["max_mag_err"], float(util.mag_err(tap["mags"][c], e2e["mags"]).max()))
             g, o = tap["features"][c], iso["features"]
             case["floor_mismatch"] += int(not np.array_equal(tap["dbg_floor"][c], iso["floor"]))
@@ -79,7 +93,7 @@ def main():
                                                             / rd["effective_gain"]))}
     out["seconds"] = time.time() - t0
     out["hard_failures"] = int(sum(c["floor_mismatch"] + c["peak_mismatch"] + c["burst_mismatch"] + c["maxex_mismatch"]
-                                   + c["pitch_hard_mismatch"] + c["prod_vs_tap_mismatch"] for c in out["cases"])
+                                   + c["pitch_hard_mismatch"] + c["prod_vs_tap_mismatch"] + c["e2e_unexplained"] for c in out["cases"])
                                + (0 if out["conditioning"]["filter_gate_bit_exact"] else 1))
     print(json.dumps(out))
 
