@@ -43,6 +43,7 @@ import numpy as np
 SLACK = 2.0          # linearisation head-room on the measured magnitude difference
 SLACK_STATE = 8.0    # a floor value is "materially different" beyond this many D_t (EMAs of magnitudes carry
                      # at most ~1.3 D_t when no branch flipped; the volatility-dependent alpha adds a few)
+ULPS = 8.0 * 2.0 ** -24   # the f32 recurrences round their own state: a few ulp of the operands are never material
 
 
 def _f32(x):
@@ -82,8 +83,9 @@ def explain(O, cfg, A, B, label=""):
         g1 = (m - eff) / (1.0 + fs)
         g2 = (m - mL) / 2.0
         g3 = (m - mR) / 2.0
-        rob_true = (g1 > thr) & (g2 > thr) & (g3 > thr)
-        rob_false = (g1 < -thr) | (g2 < -thr) | (g3 < -thr)
+        thr1 = thr + ULPS * np.maximum(m, eff)
+        rob_true = (g1 > thr1) & (g2 > thr) & (g3 > thr)
+        rob_false = (g1 < -thr1) | (g2 < -thr) | (g3 < -thr)
         peak_tie = ~(rob_true | rob_false) & in_range[None, :]
 
         # pitch-floor branch (stft.rs:351): fl = floor before the update, vol after it
@@ -91,12 +93,14 @@ def explain(O, cfg, A, B, label=""):
         vol = A["pitch_vol"].astype(np.float64)
         a_gap = (m - 1.5 * np.maximum(fl, 0.01)) / (1.0 + 1.5 * (fl > 0.01))
         b_gap = (vol - 0.15 * np.maximum(m, 0.05)) / (2.0 + 0.15 * (m > 0.05))
-        sus_true = (a_gap > thr) & (b_gap < -thr)
-        sus_false = (a_gap < -thr) | (b_gap > thr)
+        thra = thr + ULPS * np.maximum(m, fl)
+        thrb = thr + ULPS * np.maximum(vol, m)
+        sus_true = (a_gap > thra) & (b_gap < -thrb)
+        sus_false = (a_gap < -thra) | (b_gap > thrb)
         sus_tie = ~(sus_true | sus_false)
         sus_tie[0] = False                                # first frame: plain initialisation (:326-331)
 
-        taintP = np.abs(nfA - nfB) > thr_state
+        taintP = np.abs(nfA - nfB) > thr_state + ULPS * np.maximum(nfA, nfB)
         startP = taintP.copy()
         startP[1:] &= ~taintP[:-1]
         bad_start = startP & ~sus_tie
@@ -147,8 +151,8 @@ def explain(O, cfg, A, B, label=""):
             out["unexplained"] += len(off)
             out["detail"] += [("burst-count-vs-state", int(t), -1) for t in off[:5]]
         gap = (mA - 2.5 * np.maximum(fA, eps_floor)) / (1.0 + 2.5 * 1.3 * (fA > eps_floor))
-        burst_tie = np.abs(gap) <= thr
-        taintO_post = np.abs(onA - onB) > thr_state * 1.3                    # state after frame t
+        burst_tie = np.abs(gap) <= thr + ULPS * np.maximum(mA, 2.5 * fA)
+        taintO_post = np.abs(onA - onB) > thr_state * 1.3 + ULPS * np.maximum(onA, onB)    # state after frame t
         taintO_pre = np.concatenate([np.zeros_like(taintO_post[:1]), taintO_post[:-1]], axis=0)
         burst_diff = bA != bB
         bad_burst = burst_diff & ~(burst_tie | taintO_pre)
