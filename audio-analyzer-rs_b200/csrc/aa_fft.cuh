@@ -23,8 +23,19 @@ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
-    // a.x * (b.x, b.y) + a.y * (-b.y, b.x)
-    return __ffma2_rn(make_float2(a.x, a.x), b, __fmul2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x)));
+    // a.x * (b.x, b.y) + a.y * (-b.y, b.x).  The half-negation must sit on the FFMA2 ADDEND (a free `.NP` operand
+    // modifier): FMUL2 has no per-half negation, so negating b.y inside the multiply costs a MOV + FADD to build the
+    // pair (-b.y, b.x) in registers -- four instructions per complex multiply instead of two.  RN(-x) == -RN(x), so
+    // the result is bit-identical either way.
+    const float2 t = __fmul2_rn(make_float2(a.y, a.y), make_float2(b.y, b.x));     // (a.y b.y, a.y b.x)
+    return __ffma2_rn(make_float2(a.x, a.x), b, make_float2(-t.x, t.y));
+}
+// a * (cx + i cy) with a compile-time constant factor: the constants ride as scalar-broadcast immediates of FMUL2 /
+// FFMA2 (two instructions; cmul() with a constant pair makes ptxas materialise the pair in registers first)
+__device__ __forceinline__ float2 cmul_const(float2 a, float cx, float cy)
+{
+    const float2 t = __fmul2_rn(make_float2(a.y, a.x), make_float2(cy, cy));       // (a.y cy, a.x cy)
+    return __ffma2_rn(a, make_float2(cx, cx), make_float2(-t.x, t.y));
 }
 __device__ __forceinline__ float2 cmul_negi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
 __device__ __forceinline__ float2 cmul_posi(float2 a) { return make_float2(-a.y, a.x); }  // a * (+i)
@@ -124,13 +135,13 @@ struct Bfly<16> {
         // o[k] *= exp(-2 pi i k / 16) = (cos(k pi/8), -sin(k pi/8))
         float2 w[8];
         w[0] = o[0];
-        w[1] = cmul(o[1], make_float2(C1, -S1));
+        w[1] = cmul_const(o[1], C1, -S1);
         w[2] = cscale(cadd(o[2], cmul_negi(o[2])), C);
-        w[3] = cmul(o[3], make_float2(S1, -C1));
+        w[3] = cmul_const(o[3], S1, -C1);
         w[4] = cmul_negi(o[4]);
-        w[5] = cmul(o[5], make_float2(-S1, -C1));
+        w[5] = cmul_const(o[5], -S1, -C1);
         w[6] = cscale(cadd(o[6], cmul_posi(o[6])), -C);
-        w[7] = cmul(o[7], make_float2(-C1, -S1));
+        w[7] = cmul_const(o[7], -C1, -S1);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             x[k] = cadd(e[k], w[k]);
@@ -355,7 +366,9 @@ __device__ __forceinline__ void rfft_postpass(float2 a, float2 b, float2 tw, flo
     const float2 P = cadd(a, bc);                 // (sum_re, diff_im)
     const float2 Q = csub(a, bc);                 // (diff_re, sum_im)
     // ot = sum_im * tw + diff_re * (tw.y, -tw.x)
-    const float2 ot = __ffma2_rn(make_float2(Q.y, Q.y), tw, __fmul2_rn(make_float2(Q.x, Q.x), make_float2(tw.y, -tw.x)));
+    // (negation on the FFMA2 addend, not inside the FMUL2: see cmul)
+    const float2 tq = __fmul2_rn(make_float2(Q.x, Q.x), make_float2(tw.y, tw.x));
+    const float2 ot = __ffma2_rn(make_float2(Q.y, Q.y), tw, make_float2(tq.x, -tq.y));
     const float2 h = make_float2(0.5f, 0.5f);
     lo = __ffma2_rn(P, h, ot);
     const float2 hc = __ffma2_rn(P, h, make_float2(-ot.x, -ot.y));   // conj(X[N/2 - k])
