@@ -172,6 +172,8 @@ def lib():
         "aa_plan_segments": (i32, [i64, i64, i32, vp]),
         "aa_analyze_device": (i32, [vp, vp, i64, i64, i64, vp, C.POINTER(_Outputs), vp]),
         "aa_analyze_host": (i32, [vp, vp, i64, i64, i64, vp, C.POINTER(_Outputs)]),
+        "aa_state_floats": (i64, [C.POINTER(Config)]),
+        "aa_analyze_device_carry": (i32, [vp, vp, i64, i64, i64, vp, C.POINTER(_Outputs), vp, vp]),
         "aa_analyzer_last_launches": (i64, [vp]),
         "aa_stream_create": (i32, [C.POINTER(Config), pvp]),
         "aa_stream_destroy": (i32, [vp]),
@@ -348,6 +350,20 @@ class Analyzer:
                                        clip_len if clip_stride is None else clip_stride,
                                        C.c_void_p(onset_in) if onset_in else None, C.byref(o),
                                        C.c_void_p(stream) if stream else None))
+
+    @property
+    def state_floats(self) -> int:
+        """Floats in one analyzer state block (aa_state_floats)."""
+        return int(lib().aa_state_floats(C.byref(self.cfg)))
+
+    def analyze_device_carry(self, clips_ptr: int, n_clips: int, clip_len: int, clip_stride: int, state_ptr: int,
+                             mags: int = 0, features: int = 0, stable: int = 0, onset_in: int = 0, stream: int = 0):
+        """aa_analyze_device_carry: clip c starts from, and leaves its final analyzer state in, the state block
+        state_ptr + c * state_floats * 4 (device memory; zeros = a fresh analyzer)."""
+        o = _Outputs(mags or None, features or None, stable or None, None, None, None)
+        _check(lib().aa_analyze_device_carry(self._h, C.c_void_p(clips_ptr), n_clips, clip_len, clip_stride,
+                                             C.c_void_p(onset_in) if onset_in else None, C.byref(o),
+                                             C.c_void_p(state_ptr), C.c_void_p(stream) if stream else None))
 
     def analyze_host_into(self, clips: np.ndarray, n_clips: int, clip_len: int, clip_stride: int,
                           mags=None, features=None, stable=None, summaries=None, dbg_floor=None,

@@ -76,7 +76,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     if failed:
         raise RuntimeError("nvcc compilation failed")
     if force or procs or _stale(so_out, objs):
-        cmd = [nvcc, "-shared", "-o", so_out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        cmd = [nvcc, "-shared", "-o", so_out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

@@ -4,6 +4,8 @@
 // There is deliberately no CPU fallback anywhere in this file: if no sm_100 device is
 // usable every create call fails with AA_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <cmath>
@@ -80,11 +82,57 @@ extern "C" AA_API aa_status aa_set_device(int32_t device)
     return AA_OK;
 }
 
+// CPUs that NVML reports as local to CUDA device `device` (its NUMA node); false if unknown.  NVML is looked up
+// at run time (dlopen), so the library has no link-time dependency on it.
+static bool gpu_local_cpus(int device, cpu_set_t *set)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), device) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    void *lib = dlopen("libnvidia-ml.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!lib) return false;
+    typedef int (*init_t)(void);
+    typedef int (*byid_t)(const char *, void **);
+    typedef int (*aff_t)(void *, unsigned, unsigned long *);
+    init_t init = (init_t)dlsym(lib, "nvmlInit_v2");
+    byid_t byid = (byid_t)dlsym(lib, "nvmlDeviceGetHandleByPciBusId_v2");
+    aff_t aff = (aff_t)dlsym(lib, "nvmlDeviceGetCpuAffinity");
+    bool ok = false;
+    void *dev = nullptr;
+    unsigned long words[16] = {0};
+    if (init && byid && aff && init() == 0 && byid(bus, &dev) == 0 && aff(dev, 16, words) == 0) {
+        CPU_ZERO(set);
+        for (int w = 0; w < 16; ++w)
+            for (int b = 0; b < 64; ++b)
+                if ((words[w] >> b) & 1ul) {
+                    CPU_SET(w * 64 + b, set);
+                    ok = true;
+                }
+    }
+    return ok;   // (NVML stays initialised and loaded for the life of the process)
+}
+
+// Pinned host memory for the host-buffer calls.  The allocation runs with the calling thread restricted to the CPUs
+// that are local to the selected GPU, so the first-touch policy puts the pinned pages on that GPU's NUMA node: on a
+// two-socket box with eight GPUs, copies from the remote socket cross the inter-socket link and the aggregate
+// host-to-device rate of eight unbound processes collapses (tools/h2d_probe.py).  AA_NO_NUMA_BIND=1 in
+// the environment switches the binding off.
 extern "C" AA_API aa_status aa_host_alloc(size_t bytes, void **out)
 {
     if (!out) return fail(AA_ERR_INVALID, "out is null");
     CU(cudaSetDevice(g_device));
-    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    cpu_set_t old_set, gpu_set, use;
+    bool bound = false;
+    if (!getenv("AA_NO_NUMA_BIND") && sched_getaffinity(0, sizeof(old_set), &old_set) == 0 &&
+        gpu_local_cpus(g_device, &gpu_set)) {
+        CPU_AND(&use, &old_set, &gpu_set);
+        if (CPU_COUNT(&use) > 0 && sched_setaffinity(0, sizeof(use), &use) == 0) bound = true;
+    }
+    const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (bound) sched_setaffinity(0, sizeof(old_set), &old_set);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaHostAlloc");
     return AA_OK;
 }
 extern "C" AA_API aa_status aa_host_free(void *p)
@@ -579,6 +627,25 @@ extern "C" AA_API aa_status aa_analyze_device(aa_analyzer *h, const float *clips
     cudaStream_t s = (cudaStream_t)stream;   // NULL = the CUDA default stream
     return analyze_device_impl(h, clips_dev, n_clips, clip_len, clip_stride, onset_in_dev, out_dev, nullptr, s,
                                &h->launches);
+}
+
+extern "C" AA_API int64_t aa_state_floats(const aa_config *cfg)
+{
+    if (!cfg || !valid_n(cfg->n)) return 0;
+    return (int64_t)state_floats(cfg->n / 2 + 1);
+}
+
+extern "C" AA_API aa_status aa_analyze_device_carry(aa_analyzer *h, const float *clips_dev, int64_t n_clips,
+                                                    int64_t clip_len, int64_t clip_stride,
+                                                    const uint8_t *onset_in_dev, const aa_outputs *out_dev,
+                                                    float *state_dev, void *stream)
+{
+    if (!h || !clips_dev || !out_dev || !state_dev || n_clips < 0 || clip_len < 0 || clip_stride < 0)
+        return fail(AA_ERR_INVALID, "aa_analyze_device_carry: bad argument");
+    CU(cudaSetDevice(h->device));
+    h->launches = 0;
+    return analyze_device_impl(h, clips_dev, n_clips, clip_len, clip_stride, onset_in_dev, out_dev, state_dev,
+                               (cudaStream_t)stream, &h->launches);
 }
 
 // format / channels: what the host buffer holds (AA_PCM_*, interleaved); mono f32 is copied straight into the

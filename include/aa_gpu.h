@@ -185,6 +185,19 @@ AA_API aa_status aa_analyze_device(aa_analyzer *h, const float *clips_dev, int64
                                    int64_t clip_len, int64_t clip_stride,
                                    const uint8_t *onset_in_dev, const aa_outputs *out_dev,
                                    void *stream);
+/* Stateful chunks of long streams (BASELINE cfg4; the reference's analyzers carry their state forever:
+ * stft.rs:209-212, 338-363, onset.rs:149-200, PitchTracker stft.rs:19-117).  aa_state_floats: size of one analyzer
+ * state block in floats (per-bin floors, volatility, previous magnitudes, FluxTracker / EMA scalars, tracks;
+ * 4*(n/2+1) + 104).  aa_analyze_device_carry is aa_analyze_device where clip c STARTS from the state block
+ * state_dev + c*aa_state_floats (an all-zero block is a fresh analyzer) and leaves its final state there, so
+ * hop-aligned chunks of one stream (chunk c+1 = the samples from frame f1 on, no warm-up) chained through one
+ * state block -- on one GPU or handed from rank to rank as a ~33 KB message -- reproduce the unchunked run bit
+ * for bit.  n_clips must not exceed the resident CTAs (148 x 3); the launch is asynchronous on `stream`. */
+AA_API int64_t   aa_state_floats(const aa_config *cfg);
+AA_API aa_status aa_analyze_device_carry(aa_analyzer *h, const float *clips_dev, int64_t n_clips,
+                                         int64_t clip_len, int64_t clip_stride,
+                                         const uint8_t *onset_in_dev, const aa_outputs *out_dev,
+                                         float *state_dev, void *stream);
 /* Same, host buffers: H2D, kernels and D2H are pipelined over clip groups. */
 AA_API aa_status aa_analyze_host(aa_analyzer *h, const float *clips_host, int64_t n_clips,
                                  int64_t clip_len, int64_t clip_stride,

@@ -250,7 +250,8 @@ def test_onset_in_drives_the_tracker(aa, O, torch_cuda):
 
 def test_chunked_stream_with_halo(aa, O, torch_cuda):
     """cfg4 shape: hop-aligned chunks with a one-window halo, expressed as overlapping clips.
-    Stateless outputs equal the unchunked run bit for bit; stateful ones restart per chunk."""
+    Stateless outputs equal the unchunked run bit for bit; stateful ones restart per chunk (see the exact and
+    warm-up modes below)."""
     import importlib
 
     sh = importlib.import_module("audio-analyzer-rs_b200.sharding")
@@ -267,9 +268,88 @@ def test_chunked_stream_with_halo(aa, O, torch_cuda):
     assert np.array_equal(ch["features"]["centroid"].reshape(-1), full["features"]["centroid"][0, :Tc])
     # the first chunk is the start of the stream: everything equal there
     assert ch["features"][0].tobytes() == full["features"][0, :96].tobytes()
-    # later chunks restart the floors: the pitch set still agrees on most frames
-    agree = (ch["features"]["n_pitches"].reshape(-1) == full["features"]["n_pitches"][0, :Tc]).mean()
-    assert agree > 0.5, agree
+
+
+def test_chunked_stream_exact_mode_is_byte_identical(aa, O, torch_cuda):
+    """cfg4 exact mode ("stateful features need serial state hand-off"): consecutive chunks alternate
+    between TWO analyzer handles (the two ranks of a 2-GPU run; tools/run_multigpu_cases.py does it over NCCL) and
+    the analyzer state block -- floors, volatility, previous magnitudes, FluxTracker / EMA scalars, PitchTracker
+    tracks, what stft.rs:209-212 / onset.rs:149-200 keep between frames -- travels with the stream as one message.
+    Every output byte equals the unchunked run, with onset_in driving the tracker across chunk boundaries."""
+    import importlib
+
+    torch = torch_cuda
+    sh = importlib.import_module("audio-analyzer-rs_b200.sharding")
+    for n, sr, total, n_chunks in ((2048, 48000.0, 400000, 7), (4096, 48000.0, 300000, 5), (256, 48000.0, 40000, 9)):
+        hop, half = n // 4, n // 2 + 1
+        x = signals.chord_vibrato(0xA0D14, sr, total) if n != 256 else signals.note_sequence(3, sr, total)
+        T = sh.total_frames(total, n, hop)
+        onset = (np.arange(T) % 41 == 7).astype(np.uint8)
+        cfg = aa.Config(n=n, sample_rate=sr)
+        full = aa.Analyzer(cfg).analyze_host(x[None, :], onset_in=onset[None, :])
+        handles = [aa.Analyzer(cfg), aa.Analyzer(cfg)]
+        xd = torch.from_numpy(x).cuda()
+        od = torch.from_numpy(onset).cuda()
+        feat = torch.zeros(T, 96, device="cuda", dtype=torch.uint8)
+        stab = torch.zeros(T, 136, device="cuda", dtype=torch.uint8)
+        mags = torch.zeros(T, half, device="cuda", dtype=torch.float32)
+        nfl = handles[0].state_floats
+        assert nfl == 4 * half + 104
+        states = [torch.zeros(nfl, device="cuda"), torch.zeros(nfl, device="cuda")]    # one block per "rank"
+        plan = sh.chunk_plan(total, n, hop, n_chunks)
+        s = torch.cuda.current_stream().cuda_stream
+
+        def run_chunk(_stream, c, state):
+            ch = plan[c]
+            handles[c % 2].analyze_device_carry(
+                xd.data_ptr() + 4 * ch.start, 1, ch.length, (ch.length + 3) & ~3, state.data_ptr(),
+                mags=mags.data_ptr() + 4 * half * ch.first_frame, features=feat.data_ptr() + 96 * ch.first_frame,
+                stable=stab.data_ptr() + 136 * ch.first_frame, onset_in=od.data_ptr() + ch.first_frame, stream=s)
+
+        # the two "ranks" interleaved in wavefront order; the hand-off is a copy from one rank's block to the other's
+        for c in range(len(plan)):
+            if c:
+                states[c % 2].copy_(states[(c - 1) % 2])
+            run_chunk(0, c, states[c % 2])
+        torch.cuda.synchronize()
+        assert feat.cpu().numpy().tobytes() == full["features"][0].tobytes(), f"n={n}: features differ"
+        assert stab.cpu().numpy().tobytes() == full["stable"][0].tobytes(), f"n={n}: stable pitches differ"
+        assert np.array_equal(mags.cpu().numpy(), full["mags"][0]), f"n={n}: magnitudes differ"
+        # the same through the generic driver on one rank (states never leave the device)
+        feat2 = torch.zeros_like(feat)
+        mags_keep, feat_keep = mags, feat
+        feat = feat2
+        log = sh.chain_chunks(1, len(plan), 0, 1, run_chunk, lambda: torch.zeros(nfl, device="cuda"))
+        torch.cuda.synchronize()
+        assert len(log) == len(plan) and feat2.cpu().numpy().tobytes() == full["features"][0].tobytes()
+
+
+def test_chunked_stream_warmup_mode_converges(aa, O, torch_cuda):
+    """cfg4 warm-up mode: chunks start `warmup_frames` early with a fresh analyzer and drop those frames.  Not
+    exact by construction; the mismatch against the unchunked run must shrink with the warm-up length and the
+    stateless outputs stay bit-identical (the table for the 1-hour stream is in DESIGN.md 4)."""
+    import importlib
+
+    sh = importlib.import_module("audio-analyzer-rs_b200.sharding")
+    n, hop, sr = 2048, 512, 48000.0
+    x = signals.chord_vibrato(0xA0D14, sr, 600000)
+    an = aa.Analyzer(aa.Config(n=n, sample_rate=sr))
+    full = an.analyze_host(x[None, :], want_mags=False)
+    ff = full["features"][0]
+    mism = {}
+    for W in (0, 16, 128, 400):
+        feats = []
+        for ch in sh.chunk_plan(len(x), n, hop, 6, warmup_frames=W):
+            r = an.analyze_host(x[None, ch.start: ch.start + ch.length], want_mags=False)
+            assert r["T"] == ch.n_frames + ch.warmup
+            feats.append(r["features"][0][ch.warmup:])
+        f = np.concatenate(feats)
+        assert np.array_equal(f["energy"], ff["energy"]) and np.array_equal(f["centroid"], ff["centroid"])
+        bad, _ = util.compare_pitch_records(f, ff)
+        mism[W] = (len(bad), int((f["burst_count"] != ff["burst_count"]).sum()))
+    print("warm-up mismatches (pitch-list frames, burst-count frames) of", len(ff), "frames:", mism)
+    assert mism[400][0] <= mism[0][0] and mism[400][1] <= mism[0][1]
+    assert mism[400][1] <= 0.01 * len(ff)
 
 
 def test_device_api_many_clips_and_summaries(aa, O, torch_cuda):

@@ -109,3 +109,106 @@ def test_summary_all_gather_gloo_world2():
         assert p.exitcode == 0
     want = [i % 251 for i in range(n_clips)]
     assert res[0] == want and res[1] == want
+
+
+def test_chunk_plan_with_warmup():
+    n, hop, total = 2048, 512, 172800
+    T = sh.total_frames(total, n, hop)
+    for k in (1, 3, 8):
+        for w in (0, 5, 64, 10 ** 6):
+            plan = sh.chunk_plan(total, n, hop, k, warmup_frames=w)
+            frames = []
+            for ch in plan:
+                assert ch.warmup == min(w, ch.first_frame)              # the first chunk has no past to warm up on
+                assert ch.start == (ch.first_frame - ch.warmup) * hop
+                assert ch.length == (ch.n_frames + ch.warmup - 1) * hop + n
+                assert ch.start >= 0 and ch.start + ch.length <= total
+                frames.extend(range(ch.first_frame, ch.first_frame + ch.n_frames))
+            assert frames == list(range(T))
+    with pytest.raises(ValueError):
+        sh.chunk_plan(total, n, hop, 4, warmup_frames=-1)
+
+
+def test_exact_schedule_is_a_topological_partition():
+    for n_streams, n_chunks, world in ((1, 7, 2), (3, 5, 2), (8, 16, 8), (2, 3, 4)):
+        seen = {}
+        for r in range(world):
+            items = sh.exact_schedule(n_streams, n_chunks, r, world)
+            waves = [s + c for s, c in items]
+            assert waves == sorted(waves)
+            for pos, (s, c) in enumerate(items):
+                assert sh.owner(c, world) == r and (s, c) not in seen
+                seen[(s, c)] = (r, s + c)
+        assert len(seen) == n_streams * n_chunks
+        # the predecessor of every item sits on an earlier wavefront
+        for (s, c), (_, wave) in seen.items():
+            if c:
+                assert seen[(s, c - 1)][1] == wave - 1
+
+
+def _fake_run_chunk(x, frames_per_chunk, out):
+    """A stand-in analyzer with the structure of the real one: per-'bin' f32 recurrences with a data-dependent
+    branch, one record per frame, state = the recurrent values."""
+    import torch
+
+    def run(s, c, state):
+        for f in range(c * frames_per_chunk, (c + 1) * frames_per_chunk):
+            v = x[s, f]
+            upd = torch.where(v > state, state + 0.1 * (v - state), state + 0.02 * (v - state))
+            state.copy_(upd)
+            out[s, f] = state.sum()
+    return run
+
+
+def _chain_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_streams, n_chunks, fpc, bins = 3, 5, 4, 16
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand((n_streams, n_chunks * fpc, bins), generator=g)
+    out = torch.zeros((n_streams, n_chunks * fpc))
+    send, recv = sh.torch_send_recv()
+    log = sh.chain_chunks(n_streams, n_chunks, rank, world, _fake_run_chunk(x, fpc, out),
+                          lambda: torch.zeros(bins), send, recv)
+    dist.all_reduce(out)            # every frame was produced by exactly one rank
+    q.put((rank, out.tolist(), log))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exact_chain_over_gloo_world2_equals_the_unchunked_run():
+    """cfg4 exact mode, host logic: chunks of several streams alternate between two ranks, the analyzer state is
+    handed over as a message, and the records equal the unchunked single-process run bit for bit."""
+    import torch
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_chain_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r: (o, lg) for r, o, lg in (q.get(timeout=120) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n_streams, n_chunks, fpc, bins = 3, 5, 4, 16
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand((n_streams, n_chunks * fpc, bins), generator=g)
+    want = torch.zeros((n_streams, n_chunks * fpc))
+    run = _fake_run_chunk(x, n_chunks * fpc, want)
+    for s in range(n_streams):
+        run(s, 0, torch.zeros(bins))               # one chunk = the whole stream
+    assert res[0][0] == want.tolist() and res[1][0] == want.tolist()
+    # every chunk after the first got its state from the other rank
+    for r in (0, 1):
+        for s, c, src in res[r][1]:
+            assert src == (None if c == 0 else 1 - r)
+    # single rank: the same driver keeps every state local
+    out1 = torch.zeros_like(want)
+    log = sh.chain_chunks(n_streams, n_chunks, 0, 1, _fake_run_chunk(x, fpc, out1), lambda: torch.zeros(bins))
+    assert out1.tolist() == want.tolist() and all(src is None for _, _, src in log)
