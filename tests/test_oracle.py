@@ -216,3 +216,64 @@ def test_onset_fired_gating(O):
         want = bool(det[t] and rising[t] and since >= 3)
         assert bool(fired[t]) == want
         since = 0 if (want or (det[t] and since < 3)) else since + 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Reference-held vectors (tools/rust_golden): outputs of the UNMODIFIED Rust crate on the signals of
+# tests/signals.py.  The build image has no Rust toolchain, so tests/golden/ref/ is empty here and the test is
+# skipped; once a maintainer with cargo commits the dumps, this is what turns "parity unpinned" into pinned.
+# ---------------------------------------------------------------------------------------------------------
+def _ref_cases():
+    import glob
+    import os
+
+    d = os.path.join(util.GOLDEN_DIR, "ref")
+    return sorted(p[:-len(".stable.npy")] for p in glob.glob(os.path.join(d, "*.stable.npy")))
+
+
+@pytest.mark.skipif(not _ref_cases(), reason="no reference-held vectors (tools/rust_golden needs cargo; parity unpinned)")
+@pytest.mark.parametrize("base", _ref_cases() or ["none"], ids=lambda p: p.split("/")[-1])
+def test_reference_vectors(O, base):
+    import os
+
+    name = os.path.basename(base)
+    d = os.path.dirname(base)
+    x = np.load(os.path.join(d, f"in_{name}.npy")).astype(np.float32)
+    sr = float(open(os.path.join(d, f"in_{name}.sr")).read())
+    # (1) FftProcessor::process_forward (realfft 3.5.0 / rustfft 6.4.1) on raw frames
+    for n in (256, 2048, 4096):
+        p = f"{base}.spectra{n}.npy"
+        if not os.path.exists(p):
+            continue
+        ref = np.load(p)
+        ref = ref[..., 0] + 1j * ref[..., 1]
+        for t in range(ref.shape[0]):
+            got = O.rfft_f32(x[t * n // 4: t * n // 4 + n])
+            assert np.abs(got - ref[t]).max() <= 1e-6 * np.abs(ref[t]).max(), (n, t)
+    # (2) the STFT::detect_pitches worker: every pushed (Vec<(freq, score)>, beat)
+    rows = np.load(f"{base}.stable.npy")
+    r = O.analyze_clip(O.make_config(2048, 512, sr, features=O.FEAT_PITCH | O.FEAT_TRACKER), x, want_mags=False)
+    st = r["stable"]
+    emitted = np.nonzero(st["n"] > 0)[0]
+    assert len(emitted) == len(rows), (len(emitted), len(rows))
+    slot_of = -(-(emitted * 512 + 2048) // 1024) - 1          # the slot whose arrival completes frame t
+    assert np.array_equal(slot_of, rows[:, 0].astype(np.int64))
+    n_ref = rows[:, 2].astype(np.int64)
+    same_n = st["n"][emitted] == n_ref
+    f_ref, s_ref = rows[:, 3::2][:, :16], rows[:, 4::2][:, :16]
+    close = util.ulp_close(st["pitch"]["freq"][emitted], f_ref, 1e-4).all(axis=1) & \
+        util.ulp_close(st["pitch"]["score"][emitted], s_ref, 1e-3).all(axis=1)
+    bad = np.nonzero(~(same_n & close))[0]
+    assert len(bad) <= 0.01 * len(rows), f"{len(bad)} of {len(rows)} pitch frames differ from the Rust crate: {bad[:10]}"
+    # (3) the OnsetDetector::detect_onsets worker: every pushed OnsetEvent
+    ev = np.load(f"{base}.onsets.npy")
+    ro = O.analyze_clip(O.make_config(256, 64, sr, features=O.FEAT_ONSET), x, want_mags=False)
+    fired = np.nonzero(ro["features"]["flags"] & O.FLAG_ONSET_FIRED)[0]
+    want_pos = fired * 64 + 128
+    got_pos = ev[:, 1].astype(np.int64)
+    assert len(set(want_pos) ^ set(got_pos)) <= max(1, 0.02 * len(got_pos)), (want_pos[:10], got_pos[:10])
+    events, _ = O.onset_events(ro["features"], 256, 64, sr, 120.0, 4096)
+    both = {int(p): float(v) for p, v in zip(got_pos, ev[:, 2])}
+    for e in events:
+        if int(e["sample_position"]) in both:
+            assert abs(both[int(e["sample_position"])] - float(e["velocity"])) <= 1e-4
