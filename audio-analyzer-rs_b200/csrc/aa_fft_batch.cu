@@ -34,7 +34,13 @@ template <int N>
 struct FwdLayout {
     static constexpr int N2 = N / 2;
     static constexpr int NT = N2 / Geo<N>::E;
-    static constexpr bool STAGE = N == 2048;
+#ifndef AA_FFT_STAGE_MIN
+#define AA_FFT_STAGE_MIN 2048      // smallest / largest length whose next frame is staged through shared memory by TMA
+#endif
+#ifndef AA_FFT_STAGE_MAX
+#define AA_FFT_STAGE_MAX 2048
+#endif
+    static constexpr bool STAGE = N >= AA_FFT_STAGE_MIN && N <= AA_FFT_STAGE_MAX;
     static constexpr int EXLEN = (padded_len(N2) + 1) & ~1;
     static constexpr size_t ex_bytes = sizeof(float2) * EXLEN;
     static constexpr size_t stage_off = 2 * ex_bytes;                       // float[N] (16-byte aligned: EXLEN is even)
@@ -68,6 +74,16 @@ __global__ void __launch_bounds__(N / 2 / Geo<N>::E, fft_min_blocks<N>()) fft_fo
         }
     }
 
+#ifndef AA_FFT_REGPF_MAX
+#define AA_FFT_REGPF_MAX 0         // lengths up to this one keep the NEXT frame's loads in flight in registers
+#endif
+    constexpr bool REGPF = !STAGE && N <= AA_FFT_REGPF_MAX;
+    float2 nx[E];
+    if (REGPF && (int64_t)blockIdx.x < batch) {
+        const float2 *src = reinterpret_cast<const float2 *>(in + (int64_t)blockIdx.x * N);
+#pragma unroll
+        for (int m = 0; m < E; ++m) nx[m] = __ldg(&src[t + m * NT]);
+    }
     for (int64_t fr = blockIdx.x; fr < batch; fr += gridDim.x) {
         float2 v[E];
         if (STAGE) {
@@ -76,6 +92,17 @@ __global__ void __launch_bounds__(N / 2 / Geo<N>::E, fft_min_blocks<N>()) fft_fo
             const float2 *src = reinterpret_cast<const float2 *>(stage);
 #pragma unroll
             for (int m = 0; m < E; ++m) v[m] = src[t + m * NT];
+        } else if (REGPF) {
+            // one-warp / two-warp CTAs are limited by the 32 CTAs an SM holds, not by registers: the loads of the
+            // next frame are issued before this frame is transformed, which doubles the bytes in flight per CTA
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = nx[m];
+            const int64_t nxt = fr + gridDim.x;
+            if (nxt < batch) {
+                const float2 *src = reinterpret_cast<const float2 *>(in + nxt * N);
+#pragma unroll
+                for (int m = 0; m < E; ++m) nx[m] = __ldg(&src[t + m * NT]);
+            }
         } else {
             const float2 *src = reinterpret_cast<const float2 *>(in + fr * N);
 #pragma unroll

@@ -493,13 +493,21 @@ def run_ours(a):
             return time.perf_counter() - t0, n_launch
 
         e2e_s, e2e_launches = timed(e2e_step)
+        # supply ceiling of this box at this GPU count: the same pinned buffer through a plain cudaMemcpy on every
+        # rank at once (tools/h2d_probe.py is the stand-alone version): e2e cannot be faster than this copy
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            aa.lib().aa_memcpy_h2d(clips.data_ptr(), h_clips.ctypes.data, h_clips.nbytes)
+        torch.cuda.synchronize()
+        h2d_probe_s = (time.perf_counter() - t0) / 2
         # device result == host-path result
         same = bool((np.frombuffer(feat[:fe].cpu().numpy().tobytes(), np.uint8)
                      == np.frombuffer(h_feat.tobytes(), np.uint8)).all())
         e2e = {"seconds": e2e_s, "launches": e2e_launches, "matches_device_path": same, "clips": ne, "frames": fe,
                "h2d": int(h_clips.nbytes),
                "d2h": int(h_feat.nbytes + (h_stab.nbytes if h_stab is not None else 0) + h_summ.nbytes),
-               "spectra_seconds": 0.0, "spectra_d2h": 0}
+               "spectra_seconds": 0.0, "spectra_d2h": 0, "h2d_probe_s": h2d_probe_s}
         # The same call with the magnitudes copied back as well (what the CPU arm produces): needs a pinned
         # host buffer of frames x (n/2+1) floats per rank, so only when the host has the memory for it
         if mags_on:
@@ -536,12 +544,13 @@ def run_ours(a):
 
     # ---- reduce over ranks (max time) -----------------------------------------------------------
     times = torch.tensor([ms, kernel_ms, e2e["seconds"] if e2e else 0.0, e2e["pcm16_seconds"] if e2e else 0.0,
-                          e2e["spectra_seconds"] if e2e else 0.0], device=dev, dtype=torch.float64)
+                          e2e["spectra_seconds"] if e2e else 0.0, e2e["h2d_probe_s"] if e2e else 0.0],
+                         device=dev, dtype=torch.float64)
     ok = torch.tensor([1.0 if (e2e and e2e["spectra_seconds"] > 0) else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    ms, kernel_ms, e2e_s, pcm_s, sp_s = (float(v) for v in times.tolist())
+    ms, kernel_ms, e2e_s, pcm_s, sp_s, probe_s = (float(v) for v in times.tolist())
 
     if rank == 0:
         total_frames = world * frames * a.steps
@@ -589,6 +598,11 @@ def run_ours(a):
                 "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                 "ms_per_step": 1e3 * e2e_s / a.steps, "launches": e2e["launches"],
                 "matches_device_path": e2e["matches_device_path"], "clips_per_gpu": e2e["clips"],
+                # the host-to-device supply ceiling measured in this run: every rank copying the same pinned input
+                # with a plain cudaMemcpy at the same time (max over ranks); e2e can at best equal it
+                "h2d_ceiling_gbs": world * e2e["h2d"] / probe_s / 1e9,
+                "h2d_ceiling_frames_per_s": world * e2e["frames"] / probe_s,
+                "frac_of_h2d_ceiling": (ef / e2e_s) / (world * e2e["frames"] / probe_s),
                 "outputs": "feature records + stable pitches + summaries (magnitudes stay on device; e2e_spectra copies them too)",
             }
             if ok.item() > 0:
