@@ -17,11 +17,70 @@ namespace aa {
 // registers keeps 1024 threads per SM resident (measured at n = 4096 / 2048 / 1024: 71 / 69 / 76 % of the HBM
 // peak without the cap, 76 / 70 / 95 % with it).  One-warp CTAs (n <= 512) are limited by the 32 CTAs an SM
 // can hold, not by registers, and lose with the cap.
+// Geometry of the batched kernels (independent of the fused analysis kernel's Geo<N>): E complex points per
+// thread, NT = N/2/E threads per frame, FPB frames per CTA.  The short lengths pack several frames into a CTA:
+// a 256-point frame is 16 threads x 8 points (two frames per warp, radix 8 * 8 * 2: three passes instead of the
+// four of a one-warp radix-4 plan, and half the warp-instructions per frame -- at n = 256 the kernel is bound by
+// issue slots, not by HBM), and four-warp CTAs lift the resident warps per SM past what 32 one-warp CTAs give.
+template <int N>
+struct BatchGeo {
+    static constexpr int E = Geo<N>::E;
+    static constexpr int FPB = 1;
+};
+#ifndef AA_FFT_E_BIG
+#define AA_FFT_E_BIG 16            // points per thread at n = 4096 / 2048: radix 16 * 16 * 8 -- three passes / two exchanges
+                                   // instead of four / three.  With E = 8 these two lengths sit at 0.78 / 0.74 of the HBM
+                                   // peak with `mio_throttle` + `short_scoreboard` on top of the stall list (ncu,
+                                   // profiles/r02): 68 KB of shared-memory traffic per 16 KB of HBM traffic puts the
+                                   // shared-memory pipe at ~2/3 of ITS peak; one exchange less, at 128 registers and
+                                   // 512 threads per SM, gives 0.90 / 0.94
+#endif
+template <>
+struct BatchGeo<4096> {
+    static constexpr int E = AA_FFT_E_BIG;
+    static constexpr int FPB = 1;
+};
+template <>
+struct BatchGeo<2048> {
+    static constexpr int E = AA_FFT_E_BIG;
+    static constexpr int FPB = 1;
+};
+#ifndef AA_FFT_PACK_SMALL
+#define AA_FFT_PACK_SMALL 1
+#endif
+#if AA_FFT_PACK_SMALL
+template <>
+struct BatchGeo<256> {
+    static constexpr int E = 8;      // NT = 16: two frames per warp
+    static constexpr int FPB = 8;    // 128 threads
+};
+template <>
+struct BatchGeo<512> {
+    static constexpr int E = 8;      // NT = 32: one frame per warp
+    static constexpr int FPB = 4;    // 128 threads
+};
+#endif
 template <int N>
 constexpr int fft_min_blocks()
 {
-    constexpr int nt = N / 2 / Geo<N>::E;
-    return nt >= 64 ? 1024 / nt : 1;
+#ifndef AA_FFT_THREADS_PER_SM
+#define AA_FFT_THREADS_PER_SM 1024
+#endif
+    constexpr int nt = N / 2 / BatchGeo<N>::E * BatchGeo<N>::FPB;
+    constexpr int per_sm = BatchGeo<N>::E >= 16 ? AA_FFT_THREADS_PER_SM / 2 : AA_FFT_THREADS_PER_SM;   // 128 / 64 registers
+    return nt >= 64 ? per_sm / nt : 1;
+}
+// barrier among the NT threads of one frame group: the whole CTA, a named barrier per group, or the warp
+template <int NT, int FPB>
+__device__ __forceinline__ void group_sync(int grp)
+{
+    if constexpr (FPB == 1) {
+        __syncthreads();
+    } else if constexpr (NT > 32) {
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NT) : "memory");
+    } else {
+        __syncwarp();
+    }
 }
 
 // Forward transform.  Optionally the next frame's samples are fetched while the current frame is transformed:
@@ -33,34 +92,36 @@ constexpr int fft_min_blocks()
 template <int N>
 struct FwdLayout {
     static constexpr int N2 = N / 2;
-    static constexpr int NT = N2 / Geo<N>::E;
+    static constexpr int E = BatchGeo<N>::E;
+    static constexpr int FPB = BatchGeo<N>::FPB;
+    static constexpr int NT = N2 / E;
 #ifndef AA_FFT_STAGE_MIN
-#define AA_FFT_STAGE_MIN 2048      // smallest / largest length whose next frame is staged through shared memory by TMA
+#define AA_FFT_STAGE_MIN 8192      // smallest / largest length whose next frame is staged through shared memory by TMA:
+#endif                             // off by default -- the staging read costs shared-memory bandwidth, which is what
+#ifndef AA_FFT_STAGE_MAX           // binds these kernels next to HBM (it won 4 % at n = 2048 only with the E = 8 plan)
+#define AA_FFT_STAGE_MAX 0
 #endif
-#ifndef AA_FFT_STAGE_MAX
-#define AA_FFT_STAGE_MAX 2048
-#endif
-    static constexpr bool STAGE = N >= AA_FFT_STAGE_MIN && N <= AA_FFT_STAGE_MAX;
+    static constexpr bool STAGE = FPB == 1 && N >= AA_FFT_STAGE_MIN && N <= AA_FFT_STAGE_MAX;
     static constexpr int EXLEN = (padded_len(N2) + 1) & ~1;
     static constexpr size_t ex_bytes = sizeof(float2) * EXLEN;
-    static constexpr size_t stage_off = 2 * ex_bytes;                       // float[N] (16-byte aligned: EXLEN is even)
+    static constexpr size_t stage_off = 2 * ex_bytes * FPB;                 // float[N] (16-byte aligned: EXLEN is even)
     static constexpr size_t total = stage_off + (STAGE ? sizeof(float) * N : 0);
 };
 
 template <int N>
-__global__ void __launch_bounds__(N / 2 / Geo<N>::E, fft_min_blocks<N>()) fft_forward_kernel(const float *__restrict__ in,
-                                                                        int64_t batch,
-                                                                        float *__restrict__ out, Tables tab)
+__global__ void __launch_bounds__(FwdLayout<N>::NT * FwdLayout<N>::FPB, fft_min_blocks<N>())
+    fft_forward_kernel(const float *__restrict__ in, int64_t batch, float *__restrict__ out, Tables tab)
 {
     using FL = FwdLayout<N>;
-    constexpr int N2 = N / 2, E = Geo<N>::E, NT = N2 / E, EH = E / 2, HALF = N2 + 1, CBIN = N2 / 2;
+    constexpr int N2 = N / 2, E = FL::E, NT = FL::NT, FPB = FL::FPB, EH = E / 2, HALF = N2 + 1, CBIN = N2 / 2;
     constexpr bool STAGE = FL::STAGE;
     extern __shared__ __align__(16) unsigned char fsm[];
-    float2 *exA = reinterpret_cast<float2 *>(fsm);
-    float2 *exB = reinterpret_cast<float2 *>(fsm + FL::ex_bytes);
+    const int grp = threadIdx.x / NT;          // frame group inside the CTA
+    const int t = threadIdx.x % NT;
+    float2 *exA = reinterpret_cast<float2 *>(fsm + (size_t)grp * 2 * FL::ex_bytes);
+    float2 *exB = reinterpret_cast<float2 *>(fsm + (size_t)grp * 2 * FL::ex_bytes + FL::ex_bytes);
     float *stage = reinterpret_cast<float *>(fsm + FL::stage_off);
     __shared__ __align__(8) uint64_t bar;
-    const int t = threadIdx.x;
     uint32_t phase = 0;
     if (STAGE) {
         if (t == 0) {
@@ -77,14 +138,18 @@ __global__ void __launch_bounds__(N / 2 / Geo<N>::E, fft_min_blocks<N>()) fft_fo
 #ifndef AA_FFT_REGPF_MAX
 #define AA_FFT_REGPF_MAX 0         // lengths up to this one keep the NEXT frame's loads in flight in registers
 #endif
-    constexpr bool REGPF = !STAGE && N <= AA_FFT_REGPF_MAX;
+    constexpr bool REGPF = !STAGE && FPB == 1 && N <= AA_FFT_REGPF_MAX;
     float2 nx[E];
     if (REGPF && (int64_t)blockIdx.x < batch) {
         const float2 *src = reinterpret_cast<const float2 *>(in + (int64_t)blockIdx.x * N);
 #pragma unroll
         for (int m = 0; m < E; ++m) nx[m] = __ldg(&src[t + m * NT]);
     }
-    for (int64_t fr = blockIdx.x; fr < batch; fr += gridDim.x) {
+    // every group of a CTA runs the same number of iterations (a warp may hold two groups); a group past the end
+    // of the batch transforms zeros and stores nothing
+    for (int64_t fr0 = (int64_t)blockIdx.x * FPB; fr0 < batch; fr0 += (int64_t)gridDim.x * FPB) {
+        const int64_t fr = fr0 + grp;
+        const bool live = fr < batch;
         float2 v[E];
         if (STAGE) {
             mbar_wait(&bar, phase);
@@ -93,8 +158,7 @@ __global__ void __launch_bounds__(N / 2 / Geo<N>::E, fft_min_blocks<N>()) fft_fo
 #pragma unroll
             for (int m = 0; m < E; ++m) v[m] = src[t + m * NT];
         } else if (REGPF) {
-            // one-warp / two-warp CTAs are limited by the 32 CTAs an SM holds, not by registers: the loads of the
-            // next frame are issued before this frame is transformed, which doubles the bytes in flight per CTA
+            // the loads of the next frame are issued before this frame is transformed: twice the bytes in flight
 #pragma unroll
             for (int m = 0; m < E; ++m) v[m] = nx[m];
             const int64_t nxt = fr + gridDim.x;
@@ -104,12 +168,12 @@ __global__ void __launch_bounds__(N / 2 / Geo<N>::E, fft_min_blocks<N>()) fft_fo
                 for (int m = 0; m < E; ++m) nx[m] = __ldg(&src[t + m * NT]);
             }
         } else {
-            const float2 *src = reinterpret_cast<const float2 *>(in + fr * N);
+            const float2 *src = reinterpret_cast<const float2 *>(in + (live ? fr : 0) * N);
 #pragma unroll
-            for (int m = 0; m < E; ++m) v[m] = __ldg(&src[t + m * NT]);
+            for (int m = 0; m < E; ++m) v[m] = live ? __ldg(&src[t + m * NT]) : make_float2(0.f, 0.f);
         }
         fft_run<N2, E, 1, 0>(
-            v, t, exA, exB, tab.tw, [] { __syncthreads(); },
+            v, t, exA, exB, tab.tw, [&] { group_sync<NT, FPB>(grp); },
             [&] {
                 // every thread holds its samples in registers: the staging buffer can take the next frame
                 const int64_t nxt = fr + gridDim.x;
@@ -123,9 +187,9 @@ __global__ void __launch_bounds__(N / 2 / Geo<N>::E, fft_min_blocks<N>()) fft_fo
 #pragma unroll
         for (int m = EH; m < E; ++m) pbuf[padidx(t + m * NT - CBIN)] = v[m];
         if (t == 0) pbuf[padidx(CBIN)] = v[0];
-        __syncthreads();
+        group_sync<NT, FPB>(grp);
 
-        float2 *dst = reinterpret_cast<float2 *>(out + fr * 2 * (int64_t)HALF);
+        float2 *dst = reinterpret_cast<float2 *>(out + (live ? fr : 0) * 2 * (int64_t)HALF);
 #pragma unroll
         for (int m = 0; m < EH; ++m) {
             const int k = t + m * NT;
@@ -133,11 +197,13 @@ __global__ void __launch_bounds__(N / 2 / Geo<N>::E, fft_min_blocks<N>()) fft_fo
             float2 lo, hi;
             rfft_postpass(v[m], b, __ldg(&tab.pt[k]), lo, hi);
             if (k == 0) { lo.y = 0.0f; hi.y = 0.0f; }   // DC / Nyquist are purely real
-            dst[k] = lo;
-            dst[N2 - k] = hi;
+            if (live) {
+                dst[k] = lo;
+                dst[N2 - k] = hi;
+            }
         }
-        if (t == 0) dst[CBIN] = make_float2(v[EH].x, -v[EH].y);
-        __syncthreads();   // pbuf / exchange buffers are reused by the next frame
+        if (t == 0 && live) dst[CBIN] = make_float2(v[EH].x, -v[EH].y);
+        group_sync<NT, FPB>(grp);   // pbuf / exchange buffers are reused by the next frame
     }
 }
 
@@ -194,12 +260,13 @@ template <int N>
 static cudaError_t launch_fwd(const Tables &tab, const float *in, int64_t batch, float *out, int num_sms,
                               cudaStream_t s)
 {
-    constexpr int NT = N / 2 / Geo<N>::E;
-    int per_sm = 2048 / NT;
+    using FL = FwdLayout<N>;
+    constexpr int NTHREADS = FL::NT * FL::FPB;
+    int per_sm = 2048 / NTHREADS;
     if (per_sm > 16) per_sm = 16;
     int64_t grid = (int64_t)num_sms * per_sm;
-    if (grid > batch) grid = batch;
-    using FL = FwdLayout<N>;
+    const int64_t need = (batch + FL::FPB - 1) / FL::FPB;
+    if (grid > need) grid = need;
     static std::atomic<unsigned long long> configured{0ull};     // the opt-in shared-memory size is a per-device attribute
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -209,7 +276,7 @@ static cudaError_t launch_fwd(const Tables &tab, const float *in, int64_t batch,
         if (e != cudaSuccess) return e;
         if (dev < 64) configured.fetch_or(1ull << dev, std::memory_order_release);
     }
-    fft_forward_kernel<N><<<(unsigned)grid, NT, FL::total, s>>>(in, batch, out, tab);
+    fft_forward_kernel<N><<<(unsigned)grid, NTHREADS, FL::total, s>>>(in, batch, out, tab);
     return cudaGetLastError();
 }
 
