@@ -11,6 +11,7 @@ for V in variants/libaa_gpu_*.so; do
   [ -f "$V" ] || continue
   cp audio-analyzer-rs_b200/libaa_gpu.so /tmp/keep.so
   cp $V audio-analyzer-rs_b200/libaa_gpu.so
+  [ -n "$TEST_VARIANTS" ] && { timeout -s KILL 600 python -m pytest tests/test_gpu_analyze.py tests/test_gpu_stream.py -m gpu -q --tb=line -x -p no:cacheprovider 2>&1 | tail -2; }
   timeout -s KILL 300 python bench.py $B 2>&1 | show "$(basename $V) n4096"
   timeout -s KILL 300 python bench.py $B --n 2048 --sr 44100 --seconds 10 --clips 4096 2>&1 | show "$(basename $V) n2048"
   cp /tmp/keep.so audio-analyzer-rs_b200/libaa_gpu.so
