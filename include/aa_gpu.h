@@ -18,8 +18,15 @@
  *     default stream, as everywhere in CUDA).  *_device entry points are
  *     asynchronous on that stream and ordered with the caller's other work on
  *     it; *_host entry points return when the results are in host memory.
- *   - There is no CPU fallback: with no usable sm_100 device every create call
- *     fails with AA_ERR_NO_DEVICE.
+ *   - There is no CPU fallback: with no usable sm_100 (compute capability 10.0)
+ *     device every create call fails with AA_ERR_NO_DEVICE.
+ *   - Supported geometry, narrower than the reference's: window sizes 256, 512,
+ *     1024, 2048, 4096 and hop == n / 4 (the reference's two geometries are
+ *     2048 / 512, stft.rs:169-170, and 256 / 64, onset.rs:122-123; its
+ *     FftProcessor::new plans ANY length).  Anything else is AA_ERR_UNSUPPORTED
+ *     at create time.
+ *   - aa_set_device selects the GPU for handles created afterwards BY THE CALLING
+ *     THREAD (thread-local).
  */
 #ifndef AA_GPU_H
 #define AA_GPU_H
