@@ -93,3 +93,36 @@ def test_stream_errors(aa, torch_cuda):
     assert e.value.code == -5
     st.push(np.zeros(0, np.float32))
     assert len(st.poll()) == 0
+
+
+def test_stream_push_without_polling_fails_cleanly_and_can_be_retried(aa, torch_cuda):
+    """A caller that keeps pushing without polling fills the result ring: the push that would overflow it fails
+    with AA_ERR_OVERFLOW BEFORE anything is consumed, so polling and pushing the same samples again loses and
+    duplicates nothing -- the frames still equal the offline run bit for bit (and no device buffer is overrun,
+    however often the failing push is repeated)."""
+    n, sr, slot = 1024, 48000.0, 1024
+    cfg = aa.Config(n=n, sample_rate=sr)
+    x = signals.multitone(17, sr, 400 * slot)
+    batch = aa.Analyzer(cfg).analyze_host(x[None, :], want_mags=False)
+    st = aa.Stream(cfg)
+    frames, refused, i = [], 0, 0
+    while i + slot <= len(x):
+        try:
+            st.push(x[i:i + slot])
+            i += slot
+        except aa.AAError as e:
+            assert e.code == -5                       # AA_ERR_OVERFLOW
+            refused += 1
+            for _ in range(20):                       # hammering the full ring must not corrupt anything
+                with pytest.raises(aa.AAError):
+                    st.push(x[i:i + slot])
+            got = st.poll(4096)
+            assert len(got) > 0
+            frames.append(got)
+    frames.append(st.poll(4096))
+    fr = np.concatenate(frames)
+    T = (len(x) // slot * slot - n) // (n // 4) + 1
+    assert refused >= 2, "the result ring never filled: the test did not exercise the overflow path"
+    assert len(fr) == T and np.array_equal(fr["frame_index"], np.arange(T))
+    assert fr["features"].tobytes() == batch["features"][0, :T].tobytes()
+    assert fr["stable"].tobytes() == batch["stable"][0, :T].tobytes()
