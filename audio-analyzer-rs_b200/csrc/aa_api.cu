@@ -437,6 +437,18 @@ struct aa_analyzer {
     size_t seg_state_cap = 0;                     // in floats
     int max_grid = 0;
     int64_t launches = 0;
+    // time-sliced host pipeline (analyze_host_sliced): whole-batch device arrays, raw PCM staging, carried state
+    struct Sliced {
+        float *in = nullptr, *mags = nullptr, *state = nullptr;
+        aa_frame_features *feat = nullptr;
+        aa_stable_pitches *stab = nullptr;
+        aa_clip_summary *summ = nullptr;
+        uint8_t *onset = nullptr, *raw[2] = {nullptr, nullptr};
+        size_t in_cap = 0, mags_cap = 0, state_cap = 0, feat_cap = 0, stab_cap = 0, summ_cap = 0, onset_cap = 0,
+               raw_cap[2] = {0, 0};
+        cudaEvent_t h2d_done[16] = {}, k_done[16] = {};
+        bool events = false;
+    } sl;
 };
 
 extern "C" AA_API aa_status aa_analyzer_create(const aa_config *cfg, aa_analyzer **out)
@@ -495,6 +507,10 @@ extern "C" AA_API aa_status aa_analyzer_destroy(aa_analyzer *h)
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    cudaFree(h->sl.in); cudaFree(h->sl.mags); cudaFree(h->sl.state); cudaFree(h->sl.feat); cudaFree(h->sl.stab);
+    cudaFree(h->sl.summ); cudaFree(h->sl.onset); cudaFree(h->sl.raw[0]); cudaFree(h->sl.raw[1]);
+    if (h->sl.events)
+        for (int i = 0; i < 16; ++i) { cudaEventDestroy(h->sl.h2d_done[i]); cudaEventDestroy(h->sl.k_done[i]); }
     cudaFree(h->scratch);
     cudaFree(h->work_counter);
     cudaFree(h->seg_state);
@@ -554,9 +570,12 @@ extern "C" AA_API int aa_plan_segments(int64_t T, int64_t n_clips, int resident_
     return n;
 }
 
+// out_T / out_f0: see AnalyzeParams (a time slice of longer clips writes frame f at clip * out_T + out_f0 + f); the
+// summaries are not computed for a slice (out_T != T).
 static aa_status analyze_device_impl(aa_analyzer *h, const float *clips_dev, int64_t n_clips, int64_t clip_len,
                                      int64_t clip_stride, const uint8_t *onset_in_dev, const aa_outputs *out,
-                                     float *state, cudaStream_t s, int64_t *launches)
+                                     float *state, cudaStream_t s, int64_t *launches, int64_t out_T = 0,
+                                     int64_t out_f0 = 0)
 {
     const int64_t T = aa_num_frames(&h->cfg, clip_len);
     if (n_clips == 0 || T == 0) return AA_OK;
@@ -571,6 +590,8 @@ static aa_status analyze_device_impl(aa_analyzer *h, const float *clips_dev, int
     p.clip_len = clip_len;
     p.clip_stride = clip_stride;
     p.T = T;
+    p.out_T = out_T > 0 ? out_T : T;
+    p.out_f0 = out_T > 0 ? out_f0 : 0;
     p.onset_in = onset_in_dev;
     p.mags = out->mags;
     p.features = out->features;
@@ -580,8 +601,8 @@ static aa_status analyze_device_impl(aa_analyzer *h, const float *clips_dev, int
     p.state = state;
     p.scratch = h->scratch;
     p.grid = (int)std::min<int64_t>(n_clips, h->max_grid);
-    if (state && n_clips > h->max_grid)
-        return fail(AA_ERR_INVALID, "state carry-over needs one clip per resident CTA");
+    // (with a carried state and more clips than resident CTAs the clips are dealt whole from the queue: every clip
+    // loads its state block when it is taken and stores it when it is done)
     // more clips than resident CTAs: hand them out through a device-wide queue so that every SM ends up
     // with the same amount of work to within one clip
     p.work_counter = nullptr;
@@ -608,7 +629,7 @@ static aa_status analyze_device_impl(aa_analyzer *h, const float *clips_dev, int
     }
     CU(launch_analyze(p, s));
     ++*launches;
-    if (out->summaries) {
+    if (out->summaries && p.out_T == T) {
         CU(launch_summaries(out->features, n_clips, T, out->summaries, s));
         ++*launches;
     }
@@ -673,6 +694,109 @@ static aa_status analyze_host_impl(aa_analyzer *h, const void *clips_host, int f
     return st;
 }
 
+// Time-sliced host pipeline.  The clip-group pipeline below overlaps copies and kernels across GROUPS OF CLIPS, so
+// what stays exposed after the last copy is a whole clip's serial latency (a clip is walked frame by frame: 6 ms
+// for 30 s at n = 4096) plus the records of a third of the batch.  Here the batch is cut in TIME instead: slice j
+// holds the frames [f0_j, f1_j) of EVERY clip; its new samples go up with one strided copy per slice (each input byte
+// still crosses PCIe once), its kernel starts from the analyzer state the previous slice left
+// (the carry mechanism of aa_analyze_device_carry, so the records are byte-identical to a whole-clip run) and writes
+// its records where a whole-clip launch would have put them (AnalyzeParams::out_T / out_f0); what stays exposed is
+// one slice's kernel.  The device holds the whole batch (inputs, records, optionally magnitudes).
+static aa_status analyze_host_sliced(aa_analyzer *h, const void *clips_host, int format, int channels, int64_t n_clips,
+                                     int64_t clip_len, int64_t clip_stride, const uint8_t *onset_in_host,
+                                     const aa_outputs *out_host, int64_t T, int n_slices)
+{
+    auto &S = h->sl;
+    const bool direct = format == AA_PCM_F32 && channels == 1;
+    const size_t fb = (format == AA_PCM_F32 ? 4 : 2) * (size_t)channels;       // bytes per input frame
+    const int n = h->cfg.n, hop = h->cfg.hop, half = n / 2 + 1;
+    const size_t span = (size_t)((n_clips - 1) * clip_stride + clip_len);
+    const size_t frames = (size_t)(n_clips * T);
+    const size_t sf = state_floats(half);
+    aa_status st;
+    if (!S.events) {
+        for (int i = 0; i < 16; ++i) {
+            CU(cudaEventCreateWithFlags(&S.h2d_done[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&S.k_done[i], cudaEventDisableTiming));
+        }
+        S.events = true;
+    }
+    if ((st = grow(&S.in, &S.in_cap, (span + 3) & ~(size_t)3)) != AA_OK) return st;
+    if ((st = grow(&S.state, &S.state_cap, (size_t)n_clips * sf)) != AA_OK) return st;
+    const bool want_feat = out_host->features || out_host->summaries;
+    if (want_feat && (st = grow(&S.feat, &S.feat_cap, frames)) != AA_OK) return st;
+    if (out_host->stable && (st = grow(&S.stab, &S.stab_cap, frames)) != AA_OK) return st;
+    if (out_host->mags && (st = grow(&S.mags, &S.mags_cap, frames * half)) != AA_OK) return st;
+    if (out_host->summaries && (st = grow(&S.summ, &S.summ_cap, (size_t)n_clips)) != AA_OK) return st;
+    if (onset_in_host && (st = grow(&S.onset, &S.onset_cap, frames)) != AA_OK) return st;
+    CU(cudaMemsetAsync(S.state, 0, sizeof(float) * (size_t)n_clips * sf, h->s_compute));   // fresh analyzers
+
+    for (int j = 0; j < n_slices; ++j) {
+        const int64_t f0 = T * j / n_slices, f1 = T * (j + 1) / n_slices, nf = f1 - f0;
+        // samples of a clip this slice brings: everything up to the end of its last window that is not there yet
+        const int64_t a = j == 0 ? 0 : f0 * hop + (n - hop);
+        const int64_t b = j + 1 == n_slices ? clip_len : (f1 - 1) * hop + n;
+        const int64_t width = b - a;
+        // ---- H2D ----
+        if (direct) {
+            CU(cudaMemcpy2DAsync(S.in + a, sizeof(float) * (size_t)clip_stride,
+                                 static_cast<const float *>(clips_host) + a, sizeof(float) * (size_t)clip_stride,
+                                 sizeof(float) * (size_t)width, (size_t)n_clips, cudaMemcpyHostToDevice, h->s_h2d));
+        } else {
+            const int r = j & 1;
+            if (j >= 2) CU(cudaStreamWaitEvent(h->s_h2d, S.k_done[j - 2], 0));      // its ingest kernel has read raw[r]
+            if ((st = grow(&S.raw[r], &S.raw_cap[r], (size_t)n_clips * (size_t)width * fb + 16)) != AA_OK) return st;
+            CU(cudaMemcpy2DAsync(S.raw[r], (size_t)width * fb,
+                                 static_cast<const uint8_t *>(clips_host) + (size_t)a * fb, (size_t)clip_stride * fb,
+                                 (size_t)width * fb, (size_t)n_clips, cudaMemcpyHostToDevice, h->s_h2d));
+        }
+        if (onset_in_host)
+            CU(cudaMemcpy2DAsync(S.onset + f0, (size_t)T, onset_in_host + f0, (size_t)T, (size_t)nf, (size_t)n_clips,
+                                 cudaMemcpyHostToDevice, h->s_h2d));
+        CU(cudaEventRecord(S.h2d_done[j], h->s_h2d));
+        // ---- kernels ----
+        CU(cudaStreamWaitEvent(h->s_compute, S.h2d_done[j], 0));
+        if (!direct) {
+            CU(launch_ingest(S.raw[j & 1], format, channels, n_clips, width, width, clip_stride, S.in + a, h->num_sms,
+                             h->s_compute));
+            ++h->launches;
+        }
+        aa_outputs od{};
+        od.mags = out_host->mags ? S.mags : nullptr;
+        od.features = want_feat ? S.feat : nullptr;
+        od.stable = out_host->stable ? S.stab : nullptr;
+        st = analyze_device_impl(h, S.in + f0 * hop, n_clips, (nf - 1) * hop + n, clip_stride,
+                                 onset_in_host ? S.onset : nullptr, &od, S.state, h->s_compute, &h->launches, T, f0);
+        if (st != AA_OK) return st;
+        CU(cudaEventRecord(S.k_done[j], h->s_compute));
+        // ---- D2H: the columns [f0, f1) of every clip's rows ----
+        CU(cudaStreamWaitEvent(h->s_d2h, S.k_done[j], 0));
+        if (out_host->features)
+            CU(cudaMemcpy2DAsync(out_host->features + f0, sizeof(aa_frame_features) * (size_t)T, S.feat + f0,
+                                 sizeof(aa_frame_features) * (size_t)T, sizeof(aa_frame_features) * (size_t)nf,
+                                 (size_t)n_clips, cudaMemcpyDeviceToHost, h->s_d2h));
+        if (out_host->stable)
+            CU(cudaMemcpy2DAsync(out_host->stable + f0, sizeof(aa_stable_pitches) * (size_t)T, S.stab + f0,
+                                 sizeof(aa_stable_pitches) * (size_t)T, sizeof(aa_stable_pitches) * (size_t)nf,
+                                 (size_t)n_clips, cudaMemcpyDeviceToHost, h->s_d2h));
+        if (out_host->mags)
+            CU(cudaMemcpy2DAsync(out_host->mags + (size_t)f0 * half, sizeof(float) * (size_t)T * half,
+                                 S.mags + (size_t)f0 * half, sizeof(float) * (size_t)T * half,
+                                 sizeof(float) * (size_t)nf * half, (size_t)n_clips, cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    if (out_host->summaries) {
+        CU(launch_summaries(S.feat, n_clips, T, S.summ, h->s_compute));
+        ++h->launches;
+        CU(cudaEventRecord(S.k_done[15], h->s_compute));
+        CU(cudaStreamWaitEvent(h->s_d2h, S.k_done[15], 0));
+        CU(cudaMemcpyAsync(out_host->summaries, S.summ, sizeof(aa_clip_summary) * (size_t)n_clips,
+                           cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    CU(cudaStreamSynchronize(h->s_d2h));
+    CU(cudaStreamSynchronize(h->s_compute));
+    return AA_OK;
+}
+
 static aa_status analyze_host_body(aa_analyzer *h, const void *clips_host, int format, int channels, int64_t n_clips,
                                    int64_t clip_len, int64_t clip_stride, const uint8_t *onset_in_host,
                                    const aa_outputs *out_host)
@@ -689,6 +813,21 @@ static aa_status analyze_host_body(aa_analyzer *h, const void *clips_host, int f
     if (out_host->summaries && !out_host->features)
         return fail(AA_ERR_INVALID, "summaries need the features output");
     const int half = h->cfg.n / 2 + 1;
+
+    // Large batches of non-overlapping clips go through the time-sliced pipeline (see analyze_host_sliced) as long as
+    // the device can hold the batch; AA_HOST_SLICES in the environment overrides the slice count (0 = never).
+    {
+        const char *env = getenv("AA_HOST_SLICES");
+        const int env_slices = env ? atoi(env) : -1;
+        const size_t in_bytes = sizeof(float) * (size_t)((n_clips - 1) * clip_stride + clip_len);
+        const size_t mags_bytes = out_host->mags ? sizeof(float) * (size_t)(n_clips * T) * half : 0;
+        int n_slices = env_slices >= 0 ? env_slices : (int)std::min<int64_t>(12, T / 32);
+        if (n_slices > 14) n_slices = 14;
+        if (n_slices >= 2 && !out_host->dbg_floor && !out_host->dbg_peaks && clip_stride >= clip_len &&
+            (env_slices >= 2 || in_bytes >= ((size_t)32 << 20)) && in_bytes + mags_bytes <= ((size_t)64 << 30))
+            return analyze_host_sliced(h, clips_host, format, channels, n_clips, clip_len, clip_stride, onset_in_host,
+                                       out_host, T, n_slices);
+    }
 
     // clip groups: at least ~2 waves of CTAs per group when there is enough work, at most 8 groups
     int64_t n_groups = n_clips / (2 * (int64_t)h->num_sms);

@@ -29,6 +29,10 @@ constexpr int AA_MAX_SEG = 8;
 struct AnalyzeParams {
     const float *clips;
     int64_t n_clips, clip_len, clip_stride, T;
+    // per-frame arrays (onset_in, mags, features, stable, dbg_*) are indexed clip * out_T + out_f0 + f: a launch that
+    // covers the frames [out_f0, out_f0 + T) of longer clips (a time slice of the host pipeline) writes its records
+    // where a whole-clip launch would have put them.  Whole clips: out_T = T, out_f0 = 0.
+    int64_t out_T, out_f0;
     const uint8_t *onset_in;
     float *mags;
     aa_frame_features *features;

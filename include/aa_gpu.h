@@ -199,7 +199,7 @@ AA_API aa_status aa_analyze_device(aa_analyzer *h, const float *clips_dev, int64
  * state_dev + c*aa_state_floats (an all-zero block is a fresh analyzer) and leaves its final state there, so
  * hop-aligned chunks of one stream (chunk c+1 = the samples from frame f1 on, no warm-up) chained through one
  * state block -- on one GPU or handed from rank to rank as a ~33 KB message -- reproduce the unchunked run bit
- * for bit.  n_clips must not exceed the resident CTAs (148 x 3); the launch is asynchronous on `stream`. */
+ * for bit.  Any number of clips (streams) per call; the launch is asynchronous on `stream`. */
 AA_API int64_t   aa_state_floats(const aa_config *cfg);
 AA_API aa_status aa_analyze_device_carry(aa_analyzer *h, const float *clips_dev, int64_t n_clips,
                                          int64_t clip_len, int64_t clip_stride,

@@ -488,6 +488,74 @@ def test_time_segments_equal_whole_clips(aa, O, torch_cuda):
         check_end_to_end(O, res1, 0, n, sr, x=base[1], onset_in=onset[T:2 * T].cpu().numpy(), label=f"segments n={n}")
 
 
+def test_time_sliced_host_pipeline_equals_clip_groups(aa, O, torch_cuda, monkeypatch):
+    """aa_analyze_host cuts large batches in TIME (every clip's frames [f0, f1) per slice, analyzer state carried from
+    slice to slice in HBM, records written at their whole-clip positions) so that the copies hide behind the
+    kernels; small batches go clip group by clip group.  AA_HOST_SLICES forces either path: every output byte
+    must be the same, for float32 and interleaved 16-bit stereo input, with onset_in, for slice counts that do and
+    do not divide the frame count, and with more clips than one wave of resident CTAs."""
+    for n, sr, n_clips, length, slices in ((2048, 44100.0, 6, 2048 + 512 * 100 + 40, 3), (4096, 48000.0, 3, 120000, 7),
+                                           (256, 48000.0, 1500, 256 + 64 * 63, 4)):
+        rng = np.random.default_rng(n)
+        if n_clips <= 8:
+            x = np.stack([signals.note_sequence(100 + c, sr, length) for c in range(n_clips)]).astype(np.float32)
+        else:
+            base = np.stack([signals.multitone(200 + c, sr, length) for c in range(8)]).astype(np.float32)
+            x = base[rng.integers(0, 8, n_clips)] * rng.uniform(0.1, 1.0, (n_clips, 1)).astype(np.float32)
+        an = aa.Analyzer(aa.Config(n=n, sample_rate=sr))
+        T = an.num_frames(length)
+        onset = (rng.random((n_clips, T)) < 0.03).astype(np.uint8)
+        monkeypatch.setenv("AA_HOST_SLICES", "0")
+        ref = an.analyze_host(x, onset_in=onset)
+        monkeypatch.setenv("AA_HOST_SLICES", str(slices))
+        got = an.analyze_host(x, onset_in=onset)
+        for k in ("mags", "features", "stable", "summaries"):
+            assert got[k].tobytes() == ref[k].tobytes(), f"n={n}: {k} differs between the sliced and the grouped pipeline"
+        # records only (no magnitudes), the shape the headline bench uses
+        got = an.analyze_host(x, onset_in=onset, want_mags=False, want_stable=False)
+        assert got["features"].tobytes() == ref["features"].tobytes()
+        assert got["summaries"].tobytes() == ref["summaries"].tobytes()
+        # 16-bit interleaved stereo (down-mixed on the device, reference io/mod.rs)
+        if n_clips <= 8:
+            L4 = length - length % 4
+            pcm = np.empty((n_clips, L4, 2), np.int16)
+            pcm[..., 0] = np.round(x[:, :L4] * 20000.0)
+            pcm[..., 1] = np.round(x[:, :L4] * 9000.0)
+            pcm = pcm.reshape(n_clips, 2 * L4)
+            monkeypatch.setenv("AA_HOST_SLICES", "0")
+            ref = an.analyze_host_pcm(pcm, aa.PCM_I16, 2)
+            monkeypatch.setenv("AA_HOST_SLICES", str(slices))
+            got = an.analyze_host_pcm(pcm, aa.PCM_I16, 2)
+            for k in ("mags", "features", "stable", "summaries"):
+                assert got[k].tobytes() == ref[k].tobytes(), f"n={n} pcm16x2: {k} differs"
+    monkeypatch.delenv("AA_HOST_SLICES")
+
+
+def test_state_carry_with_more_streams_than_resident_ctas(aa, O, torch_cuda):
+    """aa_analyze_device_carry with thousands of streams in one call (the clips are dealt from the device queue):
+    two chained halves equal the whole-clip launch, byte for byte."""
+    torch = torch_cuda
+    n, sr, n_clips, T = 512, 22050.0, 2600, 48
+    hop, half = n // 4, n // 2 + 1
+    length = (T - 1) * hop + n
+    rng = np.random.default_rng(5)
+    base = np.stack([signals.note_sequence(300 + c, sr, length) for c in range(8)]).astype(np.float32)
+    x = torch.from_numpy(base[rng.integers(0, 8, n_clips)] * rng.uniform(0.1, 1.0, (n_clips, 1)).astype(np.float32)).cuda()
+    an = aa.Analyzer(aa.Config(n=n, sample_rate=sr))
+    s = torch.cuda.current_stream().cuda_stream
+    ref = torch.zeros(n_clips, T, 96, device="cuda", dtype=torch.uint8)
+    an.analyze_device(x.data_ptr(), n_clips, length, length, features=ref.data_ptr(), stream=s)
+    state = torch.zeros(n_clips, an.state_floats, device="cuda")
+    parts = []
+    for f0, f1 in ((0, 20), (20, T)):
+        out = torch.zeros(n_clips, f1 - f0, 96, device="cuda", dtype=torch.uint8)
+        an.analyze_device_carry(x.data_ptr() + 4 * f0 * hop, n_clips, (f1 - f0 - 1) * hop + n, length, state.data_ptr(),
+                                features=out.data_ptr(), stream=s)
+        parts.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat(parts, dim=1), ref)
+
+
 def test_whole_clip_queue_path(torch_cuda):
     """Batches of 16 or more clips per resident CTA (and AA_SEG_MIN=0) deal whole clips from the device-wide queue.
     The segment planner reads AA_SEG_MIN once per process, so the comparison of the queue path with the static
