@@ -30,6 +30,18 @@ def main():
     buf = torch.empty(a.clips * n, dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     res = {}
+
+    def sm_clock():
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
+            return {"sm_mhz": pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
+                    "sm_max_mhz": pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)}
+        except Exception:
+            return None
+
     for agc in (False, True):
         cond = aa.Conditioner(a.sr, a.slot, agc=agc)
         n_slots = cond.num_slots(n)
@@ -45,9 +57,12 @@ def main():
             torch.cuda.synchronize()
             if r:
                 times.append(e0.elapsed_time(e1))
+            clk = sm_clock()          # right after the timed region, the GPU still at its load clocks
         ms = float(np.median(times))
         res["agc" if agc else "filters_gate"] = {"ms": ms, "samples_per_s": a.clips * n / (ms * 1e-3),
-                                                 "audio_s_per_s": a.clips * a.seconds / (ms * 1e-3)}
+                                                 "audio_s_per_s": a.clips * a.seconds / (ms * 1e-3), "all_ms": times,
+                                                 "cycles_per_sample": (ms * 1e-3 * clk["sm_mhz"] * 1e6 / n) if clk else None,
+                                                 "clocks": clk}
     # CPU oracle on a bounded sample (one core)
     from oracle import aa_oracle_py as O
 
