@@ -40,11 +40,14 @@ def oracle_batch(O, clips, sr, slot_len, agc):
     return np.stack(ys), np.stack(ds)
 
 
-@pytest.mark.parametrize("sr,slot_len", [(48000.0, 1024), (44100.0, 1024), (48000.0, 256)])
-def test_filters_and_gate_are_bit_exact(aa, O, torch_cuda, sr, slot_len):
+@pytest.mark.parametrize("sr,slot_len,n_clips", [(48000.0, 1024, 37), (44100.0, 1024, 32), (48000.0, 256, 37),
+                                                 (96000.0, 128, 65), (32000.0, 192, 5), (48000.0, 1024, 1)])
+def test_filters_and_gate_are_bit_exact(aa, O, torch_cuda, sr, slot_len, n_clips):
+    """Slot lengths that 128 divides go through the cluster pipeline (two SMs per 32 clips: full groups, a ragged last
+    group, a single clip), the others through the one-thread-per-clip kernel."""
     n = slot_len * (96 if slot_len == 1024 else 200) + 100          # + a partial slot that must stay untouched
     n -= n % 4
-    clips = make_batch(sr, n, 37, seed=1)
+    clips = make_batch(sr, n, n_clips, seed=1)
     cond = aa.Conditioner(sr, slot_len, agc=False)
     got, _ = cond.process_host(clips)
     ref, _ = oracle_batch(O, clips, sr, slot_len, agc=False)
@@ -52,6 +55,33 @@ def test_filters_and_gate_are_bit_exact(aa, O, torch_cuda, sr, slot_len):
     full = (n // slot_len) * slot_len
     assert np.array_equal(got[:, full:], clips[:, full:])
     assert not np.array_equal(got[:, :full], clips[:, :full])
+
+
+def test_gate_states_are_all_exercised(aa, O, torch_cuda):
+    """Quiet passages between loud ones at several levels around the gate threshold: samples with the gate open, held
+    and closing (gain = (envelope / threshold)^4) all occur, the hold counter expires and is re-armed, and the output
+    is still the oracle's, bit for bit."""
+    sr, L = 48000.0, 1024
+    n = L * 150
+    rng = np.random.default_rng(21)
+    t = np.arange(n) / sr
+    clips = []
+    for c in range(40):
+        level = 10.0 ** rng.uniform(-4.5, -1.0)                   # around the -50 dBFS gate threshold
+        period = rng.uniform(0.05, 0.9)
+        duty = rng.uniform(0.1, 0.9)
+        on = ((t / period) % 1.0) < duty
+        x = level * np.sin(2 * np.pi * rng.uniform(100, 3000) * t) * on + 10.0 ** rng.uniform(-6.0, -3.5) * rng.standard_normal(n)
+        clips.append(x.astype(np.float32))
+    clips = np.stack(clips)
+    got, _ = aa.Conditioner(sr, L, agc=False).process_host(clips)
+    ref, _ = oracle_batch(O, clips, sr, L, agc=False)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # the gate did close somewhere (output far below the input level) and did stay open elsewhere
+    win = 4096
+    rin = np.sqrt((clips[:, : n // win * win].reshape(40, -1, win) ** 2).mean(-1))
+    rout = np.sqrt((ref[:, : n // win * win].reshape(40, -1, win) ** 2).mean(-1))
+    assert (rout < 0.05 * rin).any() and (rout > 0.5 * rin).any()
 
 
 def check_dynamics(got, ref, max_flip=0.01):
