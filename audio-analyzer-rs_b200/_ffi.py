@@ -182,6 +182,7 @@ def lib():
         "aa_stream_signal_onset": (i32, [vp]),
         "aa_stream_poll": (i32, [vp, vp, i32, C.POINTER(i32)]),
         "aa_stream_reset": (i32, [vp]),
+        "aa_stream_probe_latency": (i32, [vp, vp, i32, i32, vp, C.POINTER(i64)]),
         "aa_synth_clips_device": (i32, [vp, i64, i64, i64, f32, u64, vp]),
         "aa_yin_device": (i32, [vp, vp, i64, i64, i64, vp, vp, vp]),
         "aa_yin_host": (i32, [vp, vp, i64, i64, i64, vp, vp]),
@@ -464,6 +465,16 @@ class Stream:
         n = C.c_int32(0)
         _check(lib().aa_stream_poll(self._h, _ptr(self._buf), max_frames, C.byref(n)))
         return self._buf[: n.value].copy()
+
+    def probe_latency(self, samples: np.ndarray, count: int):
+        """aa_stream_probe_latency: push `count` samples at a time + poll, timed inside the library (no Python in
+        the loop); returns (latency_us per push, frames polled)."""
+        x = np.ascontiguousarray(samples, np.float32)
+        n_pushes = x.shape[0] // count
+        lat = np.zeros(n_pushes, np.float64)
+        frames = C.c_int64(0)
+        _check(lib().aa_stream_probe_latency(self._h, _ptr(x), int(count), int(n_pushes), _ptr(lat), C.byref(frames)))
+        return lat, int(frames.value)
 
     def set_noise_floor_db(self, db: float):
         _check(lib().aa_stream_set_noise_floor_db(self._h, db))

@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 
+#include <atomic>
+#include <chrono>
 #include "aa_internal.h"
 
 using namespace aa;
@@ -575,7 +577,8 @@ extern "C" AA_API int aa_plan_segments(int64_t T, int64_t n_clips, int resident_
 static aa_status analyze_device_impl(aa_analyzer *h, const float *clips_dev, int64_t n_clips, int64_t clip_len,
                                      int64_t clip_stride, const uint8_t *onset_in_dev, const aa_outputs *out,
                                      float *state, cudaStream_t s, int64_t *launches, int64_t out_T = 0,
-                                     int64_t out_f0 = 0)
+                                     int64_t out_f0 = 0, unsigned long long *done_flag = nullptr,
+                                     unsigned long long done_value = 0)
 {
     const int64_t T = aa_num_frames(&h->cfg, clip_len);
     if (n_clips == 0 || T == 0) return AA_OK;
@@ -592,6 +595,8 @@ static aa_status analyze_device_impl(aa_analyzer *h, const float *clips_dev, int
     p.T = T;
     p.out_T = out_T > 0 ? out_T : T;
     p.out_f0 = out_T > 0 ? out_f0 : 0;
+    p.done_flag = done_flag;
+    p.done_value = done_value;
     p.onset_in = onset_in_dev;
     p.mags = out->mags;
     p.features = out->features;
@@ -967,19 +972,24 @@ extern "C" AA_API aa_status aa_ingest_device(const void *pcm_dev, int32_t format
 struct aa_stream {
     aa_analyzer *an = nullptr;
     int n = 0, hop = 0, half = 0;
-    // device sample buffers (ping-pong linear buffers) and host pinned staging
-    float *d_buf[2] = {nullptr, nullptr};
+    // sample ring: two linear buffers (ping-pong compaction) in pinned host memory MAPPED into the device address
+    // space -- a push is a memcpy into the ring and a kernel launch; the kernel's TMA bulk copies read the hops
+    // straight from host memory (4 KB per frame: a copy-engine transfer would cost more than the reads)
+    float *h_buf[2] = {nullptr, nullptr};   // host addresses
+    float *d_buf[2] = {nullptr, nullptr};   // the same memory as the device sees it
     int cur = 0;
-    int64_t cap = 0;          // samples per device buffer
-    int64_t rd = 0, wr = 0;   // read / write positions in d_buf[cur]
-    float *h_stage = nullptr; // pinned, cap samples
-    int64_t stage_pos = 0;
+    int64_t cap = 0;          // samples per buffer
+    int64_t rd = 0, wr = 0;   // read / write positions in buf[cur]
+    // completion: the kernel stores the launch's sequence number here (mapped host memory) after its last record
+    unsigned long long *h_done = nullptr, *m_done = nullptr;
+    unsigned long long launch_seq = 0;
+    bool need_sync = false;   // a launch went through the device-side record buffers + copies (ring wrap-around)
     // analyzer state, outputs
     float *d_state = nullptr;
     aa_frame_features *d_feat = nullptr;
     aa_stable_pitches *d_stab = nullptr;
-    uint8_t *d_onset = nullptr;
-    uint8_t *h_onset = nullptr;          // pinned
+    uint8_t *d_onset = nullptr;          // device address of h_onset
+    uint8_t *h_onset = nullptr;          // pinned, mapped
     aa_frame_features *h_feat = nullptr; // pinned ring (mapped)
     aa_stable_pitches *h_stab = nullptr; // pinned ring (mapped)
     aa_frame_features *m_feat = nullptr; // device addresses of the mapped rings
@@ -997,9 +1007,9 @@ extern "C" AA_API aa_status aa_stream_destroy(aa_stream *h)
     if (!h) return AA_OK;
     if (h->an) cudaSetDevice(h->an->device);
     if (h->s) { cudaStreamSynchronize(h->s); cudaStreamDestroy(h->s); }
-    cudaFree(h->d_buf[0]); cudaFree(h->d_buf[1]); cudaFree(h->d_state); cudaFree(h->d_feat);
-    cudaFree(h->d_stab); cudaFree(h->d_onset);
-    cudaFreeHost(h->h_stage); cudaFreeHost(h->h_onset); cudaFreeHost(h->h_feat); cudaFreeHost(h->h_stab);
+    cudaFree(h->d_state); cudaFree(h->d_feat); cudaFree(h->d_stab);
+    cudaFreeHost(h->h_buf[0]); cudaFreeHost(h->h_buf[1]); cudaFreeHost(h->h_done);
+    cudaFreeHost(h->h_onset); cudaFreeHost(h->h_feat); cudaFreeHost(h->h_stab);
     if (h->an) aa_analyzer_destroy(h->an);
     delete h;
     return AA_OK;
@@ -1018,7 +1028,7 @@ extern "C" AA_API aa_status aa_stream_create(const aa_config *cfg, aa_stream **o
     h->hop = cfg->hop;
     h->half = cfg->n / 2 + 1;
     // the reference ring is max(8192, 4*window) samples (stft.rs:171, onset.rs:124); one push may carry
-    // up to that much, the device buffer holds 8x as much so compaction is rare
+    // up to that much, a buffer holds 8x as much so compaction is rare
     const int64_t ring = std::max<int64_t>(8192, 4 * (int64_t)cfg->n);
     h->cap = 8 * ring;
     h->max_frames_per_push = ring / cfg->hop + 4;
@@ -1026,14 +1036,20 @@ extern "C" AA_API aa_status aa_stream_create(const aa_config *cfg, aa_stream **o
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     ok(cudaStreamCreateWithFlags(&h->s, cudaStreamNonBlocking));
-    ok(cudaMalloc(&h->d_buf[0], sizeof(float) * h->cap));
-    ok(cudaMalloc(&h->d_buf[1], sizeof(float) * h->cap));
+    for (int b = 0; b < 2; ++b) {
+        ok(cudaHostAlloc(&h->h_buf[b], sizeof(float) * h->cap, cudaHostAllocMapped));
+        if (e == cudaSuccess) ok(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->d_buf[b]), h->h_buf[b], 0));
+    }
+    ok(cudaHostAlloc(&h->h_done, sizeof(unsigned long long), cudaHostAllocMapped));
+    if (e == cudaSuccess) {
+        *h->h_done = 0ull;
+        ok(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->m_done), h->h_done, 0));
+    }
     ok(cudaMalloc(&h->d_state, sizeof(float) * state_floats(h->half)));
     ok(cudaMalloc(&h->d_feat, sizeof(aa_frame_features) * h->max_frames_per_push));
     ok(cudaMalloc(&h->d_stab, sizeof(aa_stable_pitches) * h->max_frames_per_push));
-    ok(cudaMalloc(&h->d_onset, h->max_frames_per_push));
-    ok(cudaHostAlloc(&h->h_stage, sizeof(float) * ring, cudaHostAllocDefault));
-    ok(cudaHostAlloc(&h->h_onset, h->max_frames_per_push, cudaHostAllocDefault));
+    ok(cudaHostAlloc(&h->h_onset, h->max_frames_per_push, cudaHostAllocMapped));
+    if (e == cudaSuccess) ok(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->d_onset), h->h_onset, 0));
     // the result ring is mapped into the device address space: the kernel writes the records of a push
     // straight into it (no device-to-host copies on the latency path) whenever they do not wrap around
     ok(cudaHostAlloc(&h->h_feat, sizeof(aa_frame_features) * h->out_cap, cudaHostAllocMapped));
@@ -1050,11 +1066,41 @@ extern "C" AA_API aa_status aa_stream_create(const aa_config *cfg, aa_stream **o
     return AA_OK;
 }
 
+// Every launch of this stream so far has written its records.  The usual case is a short spin on the completion word the
+// kernel stores into mapped host memory (PCIe writes arrive in order: records first, then the word); a launch that
+// went through device-side copies, or a word that does not arrive in 20 ms (a failed launch never stores it), takes
+// cudaStreamSynchronize, which also reports the error.
+static aa_status stream_wait(aa_stream *h)
+{
+    if (!h->need_sync) {
+        volatile unsigned long long *f = h->h_done;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            for (int i = 0; i < 256; ++i) {
+                if (*f >= h->launch_seq) {
+                    std::atomic_thread_fence(std::memory_order_acquire);
+                    return AA_OK;
+                }
+#if defined(__x86_64__) || defined(__i386__)
+                __builtin_ia32_pause();
+#endif
+            }
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(20)) break;
+        }
+    }
+    CU(cudaStreamSynchronize(h->s));
+    h->need_sync = false;
+    return AA_OK;
+}
+
 extern "C" AA_API aa_status aa_stream_reset(aa_stream *h)
 {
     if (!h) return fail(AA_ERR_INVALID, "stream is null");
     CU(cudaSetDevice(h->an->device));
     CU(cudaStreamSynchronize(h->s));
+    h->need_sync = false;
+    h->launch_seq = 0;
+    *h->h_done = 0ull;
     CU(cudaMemsetAsync(h->d_state, 0, sizeof(float) * state_floats(h->half), h->s));
     CU(cudaStreamSynchronize(h->s));
     h->rd = h->wr = 0;
@@ -1098,24 +1144,22 @@ extern "C" AA_API aa_status aa_stream_push(aa_stream *h, const float *samples, i
         if (h->wr + count > h->cap && lead + avail > h->cap)
             return fail(AA_ERR_OVERFLOW, "aa_stream_push: sample ring full (nothing was consumed)");
     }
-    // previous push fully drained (results already in the host ring) before staging is reused
-    CU(cudaStreamSynchronize(h->s));
-
-    // compact: move the unread tail to the other buffer when the linear buffer would overflow
+    // compact: move the unread tail to the other buffer when the linear buffer would overflow (the launches so far
+    // may still be reading this one: wait for them first -- once per 7 ring lengths of samples)
     if (h->wr + count > h->cap) {
+        aa_status stw = stream_wait(h);
+        if (stw != AA_OK) return stw;
         const int64_t avail = h->wr - h->rd;
         // keep the read position 16-byte aligned for the TMA bulk copy
         const int64_t rd_al = h->rd & ~(int64_t)3;
         const int64_t lead = h->rd - rd_al;
-        CU(cudaMemcpyAsync(h->d_buf[h->cur ^ 1], h->d_buf[h->cur] + rd_al, sizeof(float) * (size_t)(avail + lead),
-                           cudaMemcpyDeviceToDevice, h->s));
+        std::memcpy(h->h_buf[h->cur ^ 1], h->h_buf[h->cur] + rd_al, sizeof(float) * (size_t)(avail + lead));
         h->cur ^= 1;
         h->rd = lead;
         h->wr = lead + avail;
     }
-    std::memcpy(h->h_stage, samples, sizeof(float) * (size_t)count);
-    CU(cudaMemcpyAsync(h->d_buf[h->cur] + h->wr, h->h_stage, sizeof(float) * (size_t)count,
-                       cudaMemcpyHostToDevice, h->s));
+    // (earlier launches read below wr only, so the new samples can be written while one is still running)
+    std::memcpy(h->h_buf[h->cur] + h->wr, samples, sizeof(float) * (size_t)count);
     h->wr += count;
 
     const int64_t avail = h->wr - h->rd;
@@ -1128,10 +1172,11 @@ extern "C" AA_API aa_status aa_stream_push(aa_stream *h, const float *samples, i
     // kernel takes a null array as "no onsets" and the copy is skipped
     const bool use_onset = (h->an->cfg.features & AA_FEAT_TRACKER) != 0 && h->onset_pending;
     if (use_onset) {
+        aa_status stw = stream_wait(h);          // an earlier launch may still be reading the flag array
+        if (stw != AA_OK) return stw;
         std::memset(h->h_onset, 0, (size_t)T);
         h->h_onset[0] = 1;
         h->onset_pending = false;
-        CU(cudaMemcpyAsync(h->d_onset, h->h_onset, (size_t)T, cudaMemcpyHostToDevice, h->s));
     }
     // results: straight into the mapped host ring when the T records are contiguous there, else through the
     // device buffers and two-segment copies
@@ -1144,9 +1189,12 @@ extern "C" AA_API aa_status aa_stream_push(aa_stream *h, const float *samples, i
     const int64_t clip_len = h->n + (T - 1) * h->hop;
     int64_t launches = 0;
     aa_status st = analyze_device_impl(h->an, h->d_buf[h->cur] + h->rd, 1, clip_len, (clip_len + 3) & ~(int64_t)3,
-                                       use_onset ? h->d_onset : nullptr, &od, h->d_state, h->s, &launches);
+                                       use_onset ? h->d_onset : nullptr, &od, h->d_state, h->s, &launches, 0, 0,
+                                       h->m_done, h->launch_seq + 1);
     if (st != AA_OK) return st;
+    ++h->launch_seq;
     if (!direct) {
+        h->need_sync = true;
         CU(cudaMemcpyAsync(h->h_feat + tail, h->d_feat, sizeof(aa_frame_features) * (size_t)first,
                            cudaMemcpyDeviceToHost, h->s));
         CU(cudaMemcpyAsync(h->h_stab + tail, h->d_stab, sizeof(aa_stable_pitches) * (size_t)first,
@@ -1167,7 +1215,8 @@ extern "C" AA_API aa_status aa_stream_poll(aa_stream *h, aa_stream_frame *out, i
     *n_out = 0;
     if (h->out_count == 0 || max <= 0) return AA_OK;
     CU(cudaSetDevice(h->an->device));
-    CU(cudaStreamSynchronize(h->s));
+    aa_status stw = stream_wait(h);
+    if (stw != AA_OK) return stw;
     int32_t n = (int32_t)std::min<int64_t>(max, h->out_count);
     for (int32_t i = 0; i < n; ++i) {
         const int64_t idx = (h->out_head + i) % h->out_cap;
@@ -1179,6 +1228,27 @@ extern "C" AA_API aa_status aa_stream_poll(aa_stream *h, aa_stream_frame *out, i
     h->out_count -= n;
     h->frame_index += n;
     *n_out = n;
+    return AA_OK;
+}
+
+extern "C" AA_API aa_status aa_stream_probe_latency(aa_stream *h, const float *samples, int32_t count, int32_t n_pushes,
+                                                    double *latency_us, int64_t *frames_out)
+{
+    if (!h || !samples || !latency_us || count <= 0 || n_pushes < 0)
+        return fail(AA_ERR_INVALID, "aa_stream_probe_latency: bad argument");
+    std::vector<aa_stream_frame> buf((size_t)h->max_frames_per_push + 1);
+    int64_t frames = 0;
+    for (int32_t i = 0; i < n_pushes; ++i) {
+        const auto t0 = std::chrono::steady_clock::now();
+        aa_status st = aa_stream_push(h, samples + (size_t)i * (size_t)count, count);
+        if (st != AA_OK) return st;
+        int32_t got = 0;
+        st = aa_stream_poll(h, buf.data(), (int32_t)buf.size(), &got);
+        if (st != AA_OK) return st;
+        latency_us[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        frames += got;
+    }
+    if (frames_out) *frames_out = frames;
     return AA_OK;
 }
 

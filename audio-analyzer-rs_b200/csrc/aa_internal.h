@@ -58,6 +58,10 @@ struct AnalyzeParams {
     float global_floor;      // stft.rs:323-324
     int min_bin, max_bin;    // stft.rs:454-455
     uint32_t features_mask;
+    // streaming (one clip, one CTA): after the last record has been written the kernel stores done_value to done_flag
+    // (mapped host memory, system-scope fence first), so the host can spin on it instead of synchronising the stream
+    unsigned long long *done_flag;
+    unsigned long long done_value;
 };
 
 cudaError_t launch_analyze(const AnalyzeParams &p, cudaStream_t s);

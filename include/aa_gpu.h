@@ -205,7 +205,9 @@ AA_API aa_status aa_analyze_device_carry(aa_analyzer *h, const float *clips_dev,
                                          int64_t clip_len, int64_t clip_stride,
                                          const uint8_t *onset_in_dev, const aa_outputs *out_dev,
                                          float *state_dev, void *stream);
-/* Same, host buffers: H2D, kernels and D2H are pipelined over clip groups. */
+/* Same, host buffers: H2D, kernels and D2H are pipelined -- over time slices of every clip for large batches (the
+ * analyzer state is carried from slice to slice in device memory, outputs are byte-identical to a whole-clip launch),
+ * over clip groups for small ones. */
 AA_API aa_status aa_analyze_host(aa_analyzer *h, const float *clips_host, int64_t n_clips,
                                  int64_t clip_len, int64_t clip_stride,
                                  const uint8_t *onset_in_host, const aa_outputs *out_host);
@@ -308,8 +310,12 @@ AA_API aa_status aa_yin_host(const aa_yin_config *cfg, const float *clips_host, 
 /* ------------------------------------------------------------------------- *
  * Streaming: the thread body of STFT::detect_pitches / OnsetDetector::
  * detect_onsets with the SlotPool -> private ring hand-off (stft.rs:240-266,
- * onset.rs:216-237, audio_io/mod.rs:32-79) replaced by a pinned-host +
- * device ring.  The Rust worker thread stays; its body becomes push / poll.
+ * onset.rs:216-237, audio_io/mod.rs:32-79) replaced by rings in pinned host
+ * memory that is mapped into the device address space: a push is a memcpy into
+ * the sample ring and one kernel launch (the kernel reads the hops and writes the
+ * records straight from / to host memory, then stores a completion word there);
+ * a poll spins on that word.  The Rust worker thread stays; its body becomes
+ * push / poll.
  * ------------------------------------------------------------------------- */
 typedef struct aa_stream aa_stream;
 typedef struct aa_stream_frame {
@@ -328,6 +334,12 @@ AA_API aa_status aa_stream_signal_onset(aa_stream *h);                   /* onse
 /* Copy up to `max` completed frames (oldest first); *n_out receives the count. */
 AA_API aa_status aa_stream_poll(aa_stream *h, aa_stream_frame *out, int32_t max, int32_t *n_out);
 AA_API aa_status aa_stream_reset(aa_stream *h);
+/* Measurement helper: `n_pushes` pushes of `count` samples each (taken from samples[n_pushes * count]) through
+ * aa_stream_push + aa_stream_poll in a C loop -- what a native caller such as the Rust worker thread pays per push,
+ * without a scripting language's call overhead.  latency_us[i] = wall-clock time of push i + the poll that follows it;
+ * *frames_out = frames polled in total. */
+AA_API aa_status aa_stream_probe_latency(aa_stream *h, const float *samples, int32_t count, int32_t n_pushes,
+                                         double *latency_us, int64_t *frames_out);
 
 /* ------------------------------------------------------------------------- *
  * Input conditioning chain (the step right before the analysis path).
