@@ -828,6 +828,7 @@ static aa_status analyze_host_body(aa_analyzer *h, const void *clips_host, int f
         const size_t mags_bytes = out_host->mags ? sizeof(float) * (size_t)(n_clips * T) * half : 0;
         int n_slices = env_slices >= 0 ? env_slices : (int)std::min<int64_t>(12, T / 32);
         if (n_slices > 14) n_slices = 14;
+        if (n_slices > T) n_slices = (int)T;          // (an override may ask for more slices than there are frames)
         if (n_slices >= 2 && !out_host->dbg_floor && !out_host->dbg_peaks && clip_stride >= clip_len &&
             (env_slices >= 2 || in_bytes >= ((size_t)32 << 20)) && in_bytes + mags_bytes <= ((size_t)64 << 30))
             return analyze_host_sliced(h, clips_host, format, channels, n_clips, clip_len, clip_stride, onset_in_host,
