@@ -1041,9 +1041,9 @@ extern "C" AA_API aa_status aa_stream_create(const aa_config *cfg, aa_stream **o
         ok(cudaHostAlloc(&h->h_buf[b], sizeof(float) * h->cap, cudaHostAllocMapped));
         if (e == cudaSuccess) ok(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->d_buf[b]), h->h_buf[b], 0));
     }
-    ok(cudaHostAlloc(&h->h_done, sizeof(unsigned long long), cudaHostAllocMapped));
+    ok(cudaHostAlloc(&h->h_done, 16 * sizeof(unsigned long long), cudaHostAllocMapped));   // [0..3] completion words, [4..] profiling stamps
     if (e == cudaSuccess) {
-        *h->h_done = 0ull;
+        std::memset(h->h_done, 0, 16 * sizeof(unsigned long long));
         ok(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->m_done), h->h_done, 0));
     }
     ok(cudaMalloc(&h->d_state, sizeof(float) * state_floats(h->half)));
@@ -1075,10 +1075,13 @@ static aa_status stream_wait(aa_stream *h)
 {
     if (!h->need_sync) {
         volatile unsigned long long *f = h->h_done;
+        const int words = aa::analyze_tail_warps();          // one completion word per record-writing warp
         const auto t0 = std::chrono::steady_clock::now();
         for (;;) {
             for (int i = 0; i < 256; ++i) {
-                if (*f >= h->launch_seq) {
+                bool all = true;
+                for (int w = 0; w < words; ++w) all = all && f[w] >= h->launch_seq;
+                if (all) {
                     std::atomic_thread_fence(std::memory_order_acquire);
                     return AA_OK;
                 }
@@ -1101,7 +1104,7 @@ extern "C" AA_API aa_status aa_stream_reset(aa_stream *h)
     CU(cudaStreamSynchronize(h->s));
     h->need_sync = false;
     h->launch_seq = 0;
-    *h->h_done = 0ull;
+    std::memset(h->h_done, 0, 16 * sizeof(unsigned long long));
     CU(cudaMemsetAsync(h->d_state, 0, sizeof(float) * state_floats(h->half), h->s));
     CU(cudaStreamSynchronize(h->s));
     h->rd = h->wr = 0;
@@ -1231,6 +1234,10 @@ extern "C" AA_API aa_status aa_stream_poll(aa_stream *h, aa_stream_frame *out, i
     *n_out = n;
     return AA_OK;
 }
+
+#ifdef AA_STREAM_PROF      // experiment only: the %globaltimer stamps of the last launch
+extern "C" AA_API const unsigned long long *aa_stream_debug_stamps(aa_stream *h) { return h ? h->h_done : nullptr; }
+#endif
 
 extern "C" AA_API aa_status aa_stream_probe_latency(aa_stream *h, const float *samples, int32_t count, int32_t n_pushes,
                                                     double *latency_us, int64_t *frames_out)

@@ -58,8 +58,9 @@ struct AnalyzeParams {
     float global_floor;      // stft.rs:323-324
     int min_bin, max_bin;    // stft.rs:454-455
     uint32_t features_mask;
-    // streaming (one clip, one CTA): after the last record has been written the kernel stores done_value to done_flag
-    // (mapped host memory, system-scope fence first), so the host can spin on it instead of synchronising the stream
+    // streaming (one clip, one CTA): tail warp w stores done_value to done_flag[w] (mapped host memory, system-scope
+    // fence first) after the records of its last frame, so the host can spin on the words instead of synchronising
+    // the stream (analyze_tail_warps() words)
     unsigned long long *done_flag;
     unsigned long long done_value;
 };
@@ -91,6 +92,7 @@ struct CondParams {
     float target_db, max_boost_db, smooth_alpha, silence_decay_alpha, active_snr_db, bootstrap_floor_db;
     int32_t slot_len;
 };
+int         analyze_tail_warps();
 size_t      cond_agc_state_floats();
 cudaError_t launch_cond_filter_gate(float *clips, int64_t n_clips, int64_t clip_stride, int64_t n_slots,
                                     const CondParams &p, float *stats, float *carry, cudaStream_t s);
