@@ -230,6 +230,29 @@ def _ref_cases():
     d = os.path.join(util.GOLDEN_DIR, "ref")
     return sorted(p[:-len(".stable.npy")] for p in glob.glob(os.path.join(d, "*.stable.npy")))
 
+def test_onset_event_stamping_reference_known_answers(O):
+    """timing.rs:728-771 (the reference's own tests of MusicalTransport): at 120 BPM and 48 kHz one second of
+    samples is two beats (`test_onset_latency_compensation`: 48 000 samples -> beat 2.0 before the latency term) and
+    with zero latencies / calibration the beat passes through unchanged (`test_calibrated_beat_zero_latency_
+    passthrough`).  The offline event stamping (zero latencies, clip start = time zero) must place an onset whose
+    window centre sits on sample 48 000 at beat 2.0, and one 480 samples earlier at 2.0 - (480 / 48000) * (120 / 60),
+    the value the reference's test expects for a 480-sample latency."""
+    n, hop, sr, bpm = 256, 32, 48000.0, 120.0
+    f_a = (48000 - n // 2) // hop                      # frame whose window centre is sample 48 000
+    f_b = (48000 - 480 - n // 2) // hop
+    assert f_a * hop + n // 2 == 48000 and f_b * hop + n // 2 == 48000 - 480
+    feat = np.zeros(f_a + 1, O.FEATURES_DTYPE)
+    for f in (f_a, f_b):
+        feat["flags"][f] = O.FLAG_ONSET_FIRED
+        feat["flux"][f] = 40.0
+    ev, cnt = O.onset_events(feat, n, hop, sr, bpm)
+    assert cnt == 2
+    assert ev["sample_position"].tolist() == [48000 - 480, 48000]
+    assert abs(ev["beat_position"][1] - 2.0) < 1e-9
+    assert abs(ev["beat_position"][0] - (2.0 - (480.0 / 48000.0) * (120.0 / 60.0))) < 1e-9
+    assert np.allclose(ev["velocity"], 0.8)            # the velocity the reference's test stamps: 40 / 50
+
+
 
 @pytest.mark.skipif(not _ref_cases(), reason="no reference-held vectors (tools/rust_golden needs cargo; parity unpinned)")
 @pytest.mark.parametrize("base", _ref_cases() or ["none"], ids=lambda p: p.split("/")[-1])
