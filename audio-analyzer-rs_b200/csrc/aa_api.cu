@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -606,6 +607,15 @@ static aa_status analyze_device_impl(aa_analyzer *h, const float *clips_dev, int
     p.state = state;
     p.scratch = h->scratch;
     p.grid = (int)std::min<int64_t>(n_clips, h->max_grid);
+    // a grid that fills the GPU may run the resident sub-blocks of an SM as one CTA (analyze_kernel's SUBS; identical
+    // results) IF the library was built with packed sub-blocks (AA_DEF_SUBS_4096 / AA_DEF_SUBS_2048: an experiment
+    // build, off by default -- measured neutral).  AA_NO_PACK=1 in the environment (read per full-grid launch) is the
+    // other arm of that A/B: one sub-block per CTA in the same build.
+    p.packed = 0;
+    if (p.grid == h->max_grid) {
+        const char *np = getenv("AA_NO_PACK");
+        p.packed = (np && np[0] == '1') ? 0 : 1;
+    }
     // (with a carried state and more clips than resident CTAs the clips are dealt whole from the queue: every clip
     // loads its state block when it is taken and stores it when it is done)
     // more clips than resident CTAs: hand them out through a device-wide queue so that every SM ends up

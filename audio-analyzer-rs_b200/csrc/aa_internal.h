@@ -42,6 +42,8 @@ struct AnalyzeParams {
     float *state;            // [n_clips][state_floats(half)] or nullptr
     unsigned char *scratch;  // [grid][analyze_scratch_bytes(n)] overflow space for frames with > 256 candidates
     int grid;                // persistent CTAs: min(n_clips, num_sms * analyze_ctas_per_sm(n))
+    int packed;              // the grid fills the GPU: the resident sub-blocks of an SM may be launched as one CTA
+                             // (analyze_kernel's SUBS; scratch and the static item order stay per sub-block)
     unsigned long long *work_counter;   // device-wide work queue (zeroed before the launch) or nullptr = static
     // Time segments (batch mode with more clips than resident CTAs): a work item is (clip, segment), items are
     // dealt segment-major from the queue, and a segment hands the analyzer state to the next one through

@@ -9,9 +9,10 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "audio-analyzer-rs_b200", "build", "aa_analyze.o")
-KERNELS = {   # production instantiations of the two headline window sizes (pitch + onset, LIVE = 2)
-    4096: "_ZN2aa14analyze_kernelILi4096ELb1ELb1ELb0ELi2EEEvNS_13AnalyzeParamsE",
-    2048: "_ZN2aa14analyze_kernelILi2048ELb1ELb1ELb0ELi2EEEvNS_13AnalyzeParamsE",
+KERNELS = {   # production instantiations of the two headline window sizes (pitch + onset, LIVE = 2, one
+    # sub-block per CTA; the packed form, SUBS > 1, is an opt-in experiment build)
+    (4096, 1): "_ZN2aa14analyze_kernelILi4096ELb1ELb1ELb0ELi2ELi1EEEvNS_13AnalyzeParamsE",
+    (2048, 1): "_ZN2aa14analyze_kernelILi2048ELb1ELb1ELb0ELi2ELi1EEEvNS_13AnalyzeParamsE",
 }
 
 
@@ -27,9 +28,9 @@ def _sass(kernel):
     return ins
 
 
-@pytest.mark.parametrize("n", sorted(KERNELS))
-def test_frame_loop_of_the_analysis_kernel(n):
-    ins = _sass(KERNELS[n])
+@pytest.mark.parametrize("n,subs", sorted(KERNELS))
+def test_frame_loop_of_the_analysis_kernel(n, subs):
+    ins = _sass(KERNELS[(n, subs)])
     start = next(i for i, s in enumerate(ins) if "SYNCS.PHASECHK" in s)           # hop mbarrier wait
     end = next(i for i, s in enumerate(ins) if i > start and "BAR.ARV" in s)       # FULL hand-off to the tail
     loop = ins[start:end + 1]
