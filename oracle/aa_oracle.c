@@ -777,6 +777,24 @@ void aao_onset_destroy(aao_onset *s)
 
 const float *aao_onset_floor(const aao_onset *s) { return s->noise_floor_per_bin; }
 
+/* the gates an onset has to pass before it is pushed (onset.rs:153 multiplier, :79 threshold floor, :356 burst gates,
+ * :403 / :535 re-fire guard); exported so that tests can hold them against what the real crate logged
+ * (tests/golden/ref_log_onsets.json) */
+#define AAO_FLUX_MULTIPLIER      1.5f
+#define AAO_FLUX_THRESHOLD_FLOOR 0.9f
+#define AAO_EXCESS_GATE          3.0f
+#define AAO_COUNT_GATE           3u
+#define AAO_REFIRE_FRAMES        3u
+void aao_onset_gates(float *flux_multiplier, float *flux_threshold_floor, float *excess_gate, uint32_t *count_gate,
+                     uint32_t *refire_frames)
+{
+    *flux_multiplier = AAO_FLUX_MULTIPLIER;
+    *flux_threshold_floor = AAO_FLUX_THRESHOLD_FLOOR;
+    *excess_gate = AAO_EXCESS_GATE;
+    *count_gate = AAO_COUNT_GATE;
+    *refire_frames = AAO_REFIRE_FRAMES;
+}
+
 void aao_onset_reset(aao_onset *s)
 {
     memset(s->prev_magnitude, 0, sizeof(float) * (size_t)s->half);
@@ -794,7 +812,7 @@ void aao_onset_frame(aao_onset *s, const float *current_mags, float global_floor
     const float ENERGY_EMA_RISE = 0.84f, ENERGY_EMA_DECAY = 0.95f;       /* :161-162 */
     const float BIN_BURST_RATIO = 2.5f, FLOOR_OVERCOMPENSATE = 1.3f;     /* :177-178 */
     const float FLOOR_RISE = 0.1f, FLOOR_DECAY = 0.04f;                  /* :179-180 */
-    const float multiplier = 1.5f, rise_memory = 0.84f, decay_memory = 0.89f; /* :153 */
+    const float multiplier = AAO_FLUX_MULTIPLIER, rise_memory = 0.84f, decay_memory = 0.89f; /* :153 */
 
     float current_flux = 0.0f, frame_energy = 0.0f;                       /* :261-262 */
     for (int i = 0; i < half_size; ++i) {                                 /* :274-291 */
@@ -840,16 +858,16 @@ void aao_onset_frame(aao_onset *s, const float *current_mags, float global_floor
     float memory = current_flux > s->threshold ? rise_memory : decay_memory;
     int is_onset = current_flux > s->threshold;
     s->threshold = s->threshold * memory + current_flux * (1.0f - memory);
-    if (s->threshold < 0.9f) s->threshold = 0.9f;
+    if (s->threshold < AAO_FLUX_THRESHOLD_FLOOR) s->threshold = AAO_FLUX_THRESHOLD_FLOOR;
     int flux_onset = is_onset && current_flux > (s->threshold * multiplier);
 
-    int bin_burst_onset = max_bin_excess > 3.0f && bin_burst_count >= 3;  /* :356 */
+    int bin_burst_onset = max_bin_excess > AAO_EXCESS_GATE && bin_burst_count >= AAO_COUNT_GATE;  /* :356 */
     int onset_detected = flux_onset && bin_burst_onset;                   /* :357 */
     int energy_rising = frame_energy > s->energy_ema * 1.5f;              /* :373 */
     /* offline reading of :383-456 and :535-539: no metronome ticks to guard against
      * (suppressed_by_tick = false) and calibration already done */
-    int onset_fired = onset_detected && energy_rising && s->frames_since_onset >= 3;   /* :403 */
-    if (onset_fired || (onset_detected && s->frames_since_onset < 3)) s->frames_since_onset = 0;  /* :535 */
+    int onset_fired = onset_detected && energy_rising && s->frames_since_onset >= AAO_REFIRE_FRAMES;   /* :403 */
+    if (onset_fired || (onset_detected && s->frames_since_onset < AAO_REFIRE_FRAMES)) s->frames_since_onset = 0;  /* :535 */
     else if (s->frames_since_onset != 0xffffffffu) s->frames_since_onset += 1;          /* saturating_add */
 
     out->flux = current_flux;

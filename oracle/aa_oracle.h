@@ -255,6 +255,11 @@ typedef struct aao_onset_event {
 } aao_onset_event;
 int64_t   aao_onset_events(const aao_features *feat, int64_t T, int n, int hop, float sample_rate, float bpm,
                            int64_t max_events, aao_onset_event *out);
+void      aao_onset_gates(float *flux_multiplier, float *flux_threshold_floor, float *excess_gate, uint32_t *count_gate,
+                          uint32_t *refire_frames);
+void      aao_stamp_onset(double current_beats, int64_t output_frames, float bpm, float sample_rate, int64_t input_lat,
+                          int64_t output_lat, int64_t calibration, int64_t sample_offset, double *beat_position,
+                          int64_t *output_samples);
 int       aao_interval(float f_lo, float f_hi, int system, float *accuracy);
 void      aao_tuner_frame(const float *pairs, int n, int system, int single_pitch_mode, int *kind, int *best, int *lo,
                           int *hi, int *interval, float *accuracy);

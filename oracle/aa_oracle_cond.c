@@ -340,6 +340,29 @@ void aao_ingest(const void *pcm, int format, int channels, int64_t n_frames, flo
 }
 
 /* ------------------------------------------------------------------------------------------
+ * MusicalTransport::stamp_onset, audio_io/timing.rs:311-337, with the transport's atomics passed in:
+ *   beats_per_sample = bpm / (60 sr)                                              :313-315 (f64)
+ *   beat_position    = current_beats - (input_lat + output_lat) * bps + sample_offset * bps - calibration * bps
+ *                      (in this order, :326-330)
+ *   output_samples   = output_frames - input_lat - output_lat + sample_offset - calibration        :335-336
+ * sample_offset is what the detector passes: -(available_samples - window_size / 2), onset.rs:386-387.
+ * Pinned by a value the real crate logged (tests/golden/ref_log_onsets.json, from the reference's output.log).
+ * ------------------------------------------------------------------------------------------ */
+void aao_stamp_onset(double current_beats, int64_t output_frames, float bpm, float sample_rate, int64_t input_lat,
+                     int64_t output_lat, int64_t calibration, int64_t sample_offset, double *beat_position,
+                     int64_t *output_samples)
+{
+    const double sr = (double)sample_rate;
+    const double b = (double)bpm;
+    const double beats_per_sample = b / (60.0 * sr);
+    const double latency_beats = (double)(input_lat + output_lat) * beats_per_sample;
+    const double offset_beats = (double)sample_offset * beats_per_sample;
+    const double calibration_beats = (double)calibration * beats_per_sample;
+    *beat_position = current_beats - latency_beats + offset_beats - calibration_beats;
+    *output_samples = output_frames - input_lat - output_lat + sample_offset - calibration;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Offline onset events: what OnsetDetector pushes on onset_tx for every frame whose
  * gating passed (onset.rs:383-456 with no metronome ticks and calibration done = AAO_FLAG_ONSET_FIRED),
  * stamped like MusicalTransport::stamp_onset (timing.rs:311-337) with zero latencies / calibration and the

@@ -183,6 +183,11 @@ def lib():
     ip = C.POINTER(C.c_int)
     L.aao_tuner_frame.argtypes = [fp, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, fp]
     L.aao_ingest.argtypes = [vp, C.c_int, C.c_int, C.c_int64, fp]
+    L.aao_onset_gates.restype = None
+    L.aao_onset_gates.argtypes = [C.POINTER(C.c_float)] * 3 + [C.POINTER(C.c_uint32)] * 2
+    L.aao_stamp_onset.restype = None
+    L.aao_stamp_onset.argtypes = [C.c_double, C.c_int64, C.c_float, C.c_float, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                  C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.aao_onset_events.restype = C.c_int64
     L.aao_onset_events.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int64, vp]
     L.aao_cond_clip.restype = C.c_int64
@@ -437,6 +442,23 @@ def ingest(pcm: np.ndarray, fmt: int, channels: int) -> np.ndarray:
 ONSET_EVENT_DTYPE = np.dtype([("beat_position", "<f8"), ("sample_position", "<i8"), ("frame", "<i8"),
                               ("velocity", "<f4"), ("reserved", "<u4")])
 assert ONSET_EVENT_DTYPE.itemsize == 32
+
+
+def onset_gates():
+    """The gates of onset.rs:153 / :79 / :356 / :403 as the oracle applies them."""
+    a, b, c = C.c_float(), C.c_float(), C.c_float()
+    d, e = C.c_uint32(), C.c_uint32()
+    lib().aao_onset_gates(C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e))
+    return {"flux_multiplier": a.value, "flux_threshold_floor": b.value, "excess_gate": c.value,
+            "count_gate": d.value, "refire_frames": e.value}
+
+
+def stamp_onset(current_beats, output_frames, bpm, sample_rate, input_lat, output_lat, calibration, sample_offset):
+    """MusicalTransport::stamp_onset (timing.rs:311-337): (beat_position f64, output_samples i64)."""
+    bp, os_ = C.c_double(0.0), C.c_int64(0)
+    lib().aao_stamp_onset(float(current_beats), int(output_frames), float(bpm), float(sample_rate), int(input_lat),
+                          int(output_lat), int(calibration), int(sample_offset), C.byref(bp), C.byref(os_))
+    return bp.value, os_.value
 
 
 def onset_events(features: np.ndarray, n: int, hop: int, sample_rate: float, bpm: float = 120.0, max_events: int = 256):

@@ -254,6 +254,109 @@ def test_onset_event_stamping_reference_known_answers(O):
 
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Numbers the REAL crate printed (the reference's output.log, a live run of its onset detector; extracted by
+# tests/golden/extract_ref_log.py).  The audio behind them is not available, so they pin no magnitudes -- they pin
+# what can be held against a log: the f64 arithmetic of stamp_onset to the last printed digit, the window-centre
+# offsets the 256 / 64 geometry over 1024-sample slots can produce, the onset gates and the re-fire guard.
+# ---------------------------------------------------------------------------------------------------------
+def _ref_log():
+    import json
+    import os
+
+    return json.load(open(os.path.join(util.GOLDEN_DIR, "ref_log_onsets.json")))
+
+
+def _onset_offset_lattice(slot=1024, n=256, hop=64, slots=8):
+    """window_centre_offset of every frame the reference's loop produces (onset.rs:240-257 consumption loop,
+    :386-387 offset): a slot arrives, frames are cut while a window is available."""
+    avail, offs = 0, []
+    for _ in range(slots):
+        avail += slot
+        while avail >= n:
+            offs.append(-(avail - n // 2))
+            avail -= hop
+    return offs
+
+
+def test_reference_log_stamp_onset_to_the_last_digit(O):
+    """`beat_pos: 0.6653333333333337, transport beat: 0.7440000000000003, target_samples: 9600, event_samples: 15968`
+    (onset.rs:413-419) is MusicalTransport::stamp_onset (timing.rs:311-337) seen from outside.  At 120 BPM / 48 kHz
+    the transport beat is output frame 17 856, so latency - offset = 17 856 - 15 968 = 1 888 samples; whichever
+    window-centre offset the frame had, the oracle's restatement must print the same two numbers."""
+    cal = _ref_log()["calibration"]
+    cur, want = float(cal["transport_beat"]), float(cal["beat_pos"])
+    sr, bpm = 48000.0, 120.0
+    frames = round(cur * 60.0 * sr / bpm)
+    assert frames == 17856 and abs(frames * bpm / (60.0 * sr) - cur) < 1e-12
+    lat_minus_off = frames - cal["event_samples"]
+    assert lat_minus_off == 1888
+    assert cal["event_samples"] - cal["target_samples"] == cal["residual_samples"]           # onset.rs:411
+    assert f"{cal['residual_samples'] * 1000.0 / sr:.1f}" == cal["residual_ms"]              # onset.rs:412, :421
+    exact = 0
+    lattice = sorted(set(_onset_offset_lattice()))
+    for off in lattice:
+        lat = lat_minus_off + off                       # input + output latency of that split
+        assert lat > 0
+        beat, out_samples = O.stamp_onset(cur, frames, bpm, sr, lat // 2, lat - lat // 2, 0, off)
+        assert out_samples == cal["event_samples"]
+        assert abs(beat - want) <= 2.3e-16              # one ulp at 0.67
+        exact += repr(beat) == cal["beat_pos"]
+    assert exact >= len(lattice) - 1, exact             # (one split rounds the other way: -448 / 1440)
+    # another tempo does not explain the line: 17 856 output frames only follow from 120 BPM
+    for other in (60.0, 90.0, 100.0, 140.0):
+        f2 = cur * 60.0 * sr / other
+        assert abs(f2 - round(f2)) > 1e-6 or round(f2) - 1888 != cal["event_samples"]
+
+
+def test_reference_log_offsets_gates_and_refire_guard(O):
+    """The 78 `onset @ beat B (raw offset R, flux=F, burst=X/C)` lines (onset.rs:442-449): every R lies on the
+    offset lattice of the 256 / 64 geometry fed by 1024-sample slots -- and the log covers the whole lattice, both
+    extremes included; every logged onset passes the gates as the oracle applies them; onsets of one processing
+    burst are never closer than the oracle's re-fire guard allows, and their beat distance is their offset
+    distance at 120 BPM."""
+    log = _ref_log()["onsets"]
+    assert len(log) == 78
+    lattice = set(_onset_offset_lattice())
+    assert lattice == set(range(-1088, -127, 64))
+    assert {e["raw_offset"] for e in log} == lattice
+    g = O.onset_gates()
+    for e in log:
+        assert e["max_excess"] > g["excess_gate"] and e["burst_count"] >= g["count_gate"]          # onset.rs:356
+        assert e["flux"] + 0.05 > g["flux_threshold_floor"] * g["flux_multiplier"]                 # :79, :81 (1 decimal)
+    # the tightest logged values sit right at the gates: a stricter oracle would contradict the log
+    assert min(e["burst_count"] for e in log) == g["count_gate"]
+    assert min(e["max_excess"] for e in log) < g["excess_gate"] + 0.2
+    # re-fire guard: what is the closest pair of fired onsets the oracle can produce?
+    half = 129
+    closest = None
+    for gap in range(1, 8):                              # a step in level every `gap` frames
+        det = O.Onset(half)
+        level, fired = 1.0, []
+        for f in range(8 * gap + 1):
+            if f % gap == 0:
+                level *= 8.0
+            feat = det.frame(np.full(half, level, np.float32), 1e-3)
+            if feat["flags"] & O.FLAG_ONSET_FIRED:
+                fired.append(f)
+        if len(fired) > 1:
+            d = int(np.diff(fired).min())
+            closest = d if closest is None else min(closest, d)
+    assert closest == g["refire_frames"] + 1 == 4
+    bps = 120.0 / (60.0 * 48000.0)
+    same_burst = 0
+    for a, b in zip(log, log[1:]):
+        if b["t"] - a["t"] > 0.003:                      # a processing burst logs its onsets within ~2 ms
+            continue
+        frames_by_offset = (b["raw_offset"] - a["raw_offset"]) // 64
+        if abs((b["beat"] - a["beat"]) - frames_by_offset * 64 * bps) > 1.01e-4:
+            continue                                     # (the transport moved between the two log calls)
+        same_burst += 1
+        assert frames_by_offset >= closest
+    assert same_burst >= 5 and min((b["raw_offset"] - a["raw_offset"]) // 64 for a, b in zip(log, log[1:])
+                                   if 0 < b["t"] - a["t"] <= 0.003) == closest
+
+
 @pytest.mark.skipif(not _ref_cases(), reason="no reference-held vectors (tools/rust_golden needs cargo; parity unpinned)")
 @pytest.mark.parametrize("base", _ref_cases() or ["none"], ids=lambda p: p.split("/")[-1])
 def test_reference_vectors(O, base):
