@@ -12,7 +12,13 @@
  * file therefore restates the reference source line by line (citations below are
  * relative to /root/reference) and is cross-checked against an independent
  * numpy restatement (tests/golden/make_golden.py) and a float64 DFT -- not
- * against outputs of the reference binary.
+ * against outputs of the reference binary.  What the reference tree does hold is
+ * replayed on it: the known answers of its own unit tests (theory.rs:405-448,
+ * 545-604; timing.rs:728-771) and the one log of a live onset-detector run it
+ * ships (output.log -> tests/golden/ref_log_onsets.json: stamp_onset to the last
+ * printed digit, the window-centre offset lattice, the onset gates, the re-fire
+ * guard).  None of that reaches the spectra or the pitch lists: PARITY UNPINNED
+ * stands for rows a1-a12 until tools/rust_golden has been run.
  *
  * Arithmetic rules: every scalar the reference holds in f32 is held in `float`
  * here, operations are performed in the reference's order, and the file must be
