@@ -51,6 +51,9 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
             if macro.startswith("AA_DEF_") and os.environ[macro] != "":
                 extra.append(f"-DAA_{macro[len('AA_DEF_'):]}={os.environ[macro]}")
                 force = True
+        if os.environ.get("AA_NVCC_EXTRA"):      # extra nvcc flags of an experiment variant, e.g. --extra-device-vectorization
+            extra += os.environ["AA_NVCC_EXTRA"].split()
+            force = True
     objdir = os.path.join(HERE, "build") if so_out == SO else os.path.join(HERE, "build", "variant")
     os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
