@@ -644,6 +644,17 @@ static aa_status analyze_device_impl(aa_analyzer *h, const float *clips_dev, int
     }
     CU(launch_analyze(p, s));
     ++*launches;
+#ifdef AA_CHECKED
+    {   // checked build: the kernel range-checks its data-dependent indices (aa_analyze.cu: AA_CHK)
+        unsigned word = 0u;
+        CU(analyze_check_word(&word, s));
+        if (word) {
+            char msg[96];
+            snprintf(msg, sizeof msg, "checked build: index check failed in analyze_kernel, mask 0x%x", word);
+            return fail(AA_ERR_CUDA, msg);
+        }
+    }
+#endif
     if (out->summaries && p.out_T == T) {
         CU(launch_summaries(out->features, n_clips, T, out->summaries, s));
         ++*launches;

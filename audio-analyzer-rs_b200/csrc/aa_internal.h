@@ -68,6 +68,7 @@ struct AnalyzeParams {
 };
 
 cudaError_t launch_analyze(const AnalyzeParams &p, cudaStream_t s);
+cudaError_t analyze_check_word(unsigned *word, cudaStream_t s);   // -DAA_CHECKED builds: violated index checks
 size_t      analyze_smem_bytes(int n);
 int         analyze_threads(int n);
 int         analyze_ctas_per_sm(int n);
