@@ -230,6 +230,34 @@ struct OnsetEvent {            // src/audio_io/timing.rs:77-87
     float velocity;
 };
 
+// window_centre_offset of frame i of a poll that returned n frames (onset.rs:386-387:
+// -(available_samples - window_size / 2)): when the reference processed that frame, the samples still buffered behind
+// its start were its own window plus one hop for every frame that follows it in the burst.  With 1024-sample slots
+// this gives exactly the offsets -128 ... -1088 the real crate logs (tests/golden/ref_log_onsets.json).
+inline int64_t window_centre_offset(int32_t n_in_poll, int32_t i, int window_size, int hop)
+{
+    const int64_t available = window_size + static_cast<int64_t>(n_in_poll - 1 - i) * hop;
+    return -(available - window_size / 2);
+}
+
+// MusicalTransport::stamp_onset (timing.rs:311-337) over plain values, for hosts that keep the transport's atomics
+// themselves: the f64 operations in the reference's order.
+inline OnsetEvent stamp_onset_at(double current_beats, int64_t output_frames, double bpm, double sample_rate,
+                                 int64_t input_latency, int64_t output_latency, int64_t calibration,
+                                 int64_t sample_offset, float velocity)
+{
+    const double beats_per_sample = bpm / (60.0 * sample_rate);
+    const double latency_beats = static_cast<double>(input_latency + output_latency) * beats_per_sample;
+    const double offset_beats = static_cast<double>(sample_offset) * beats_per_sample;
+    const double calibration_beats = static_cast<double>(calibration) * beats_per_sample;
+    OnsetEvent ev;
+    ev.beat_position = current_beats - latency_beats + offset_beats - calibration_beats;
+    ev.raw_sample_offset = sample_offset;
+    ev.output_samples = output_frames - input_latency - output_latency + sample_offset - calibration;
+    ev.velocity = velocity;
+    return ev;
+}
+
 // The slice of MusicalTransport the onset gating needs (timing.rs): stamp_onset,
 // nearest_tick_distance_beats, get_bpm.
 struct TransportHooks {
@@ -295,8 +323,8 @@ public:
                             if (onset_detected) {                                                  // onset.rs:383-456
                                 // samples still buffered behind this frame when the reference would have
                                 // processed it: the frames of this poll that follow it, plus the window
-                                const int64_t available = window_size + static_cast<int64_t>(n - 1 - i) * hop;
-                                const int64_t window_centre_offset = -(available - window_size / 2);
+                                const int64_t window_centre_offset =
+                                    audio_engine_gpu::window_centre_offset(n, i, window_size, hop);
                                 float velocity = f.flux > f.max_excess * 5.0f ? f.flux : f.max_excess * 5.0f;
                                 velocity = velocity / 50.0f;
                                 velocity = velocity < 0.0f ? 0.0f : (velocity > 1.0f ? 1.0f : velocity);

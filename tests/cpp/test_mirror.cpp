@@ -33,6 +33,21 @@ int main(int argc, char **argv)
         } catch (const Error &e) {
             if (e.code != AA_ERR_UNSUPPORTED) return fail("wrong error code for bad length");
         }
+        // ---- host-side onset stamping against what the real crate logged (tests/golden/ref_log_onsets.json, from the
+        // reference's output.log): a 1024-sample slot behind a 192-sample leftover is a poll of 16 frames whose
+        // window-centre offsets run from -1088 to -128; the first slot of a stream gives 13 frames from -896 ----
+        if (window_centre_offset(16, 0, 256, 64) != -1088 || window_centre_offset(16, 15, 256, 64) != -128 ||
+            window_centre_offset(13, 0, 256, 64) != -896 || window_centre_offset(16, 7, 256, 64) != -640)
+            return fail("window_centre_offset lattice");
+        // `beat_pos: 0.6653333333333337, transport beat: 0.7440000000000003, ... event_samples: 15968` (onset.rs:413-419)
+        // at 120 BPM / 48 kHz: output frame 17 856, latency - offset = 1 888 samples
+        {
+            const OnsetEvent ev = stamp_onset_at(0.7440000000000003, 17856, 120.0, 48000.0, 400, 400, 0, -1088, 0.5f);
+            if (ev.output_samples != 15968 || ev.beat_position != 0.6653333333333337 || ev.raw_sample_offset != -1088)
+                return fail("stamp_onset_at against the reference's log line");
+            std::printf("ok: stamp_onset_at reproduces the logged beat %.16f / sample %lld\n", ev.beat_position,
+                        static_cast<long long>(ev.output_samples));
+        }
         return 0;
     }
 

@@ -25,6 +25,8 @@ def test_cpp_mirror_compiles_and_fails_loudly_without_device(aa, tmp_path):
     out = subprocess.run([exe, "nodevice"], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0, out.stderr
     assert "no CPU fallback" in out.stdout
+    # host-side onset stamping (no device needed): the offsets and the f64 beat the real crate logged
+    assert "stamp_onset_at reproduces the logged beat 0.6653333333333337 / sample 15968" in out.stdout
 
 
 @pytest.mark.gpu
